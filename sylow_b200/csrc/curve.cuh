@@ -1,0 +1,171 @@
+// G1 = E(Fp): y^2 = x^3 + 3 and G2 in E'(Fp2): y^2 = x^3 + 3/(9+u), homogeneous projective
+// coordinates with the complete a = 0 formulas of Renes-Costello-Batina (eprint 2015/1060 Algs 7, 9).
+//
+// Value-level replacement of /root/reference/src/groups/group.rs:339-386 (double), :528-599 (add),
+// :639-667 (scalar multiplication by an Fp-range scalar) and :475-495 (projective -> affine).  Parity
+// is defined on AFFINE coordinates, so the scalar multiplication is free to use a
+// fixed 4-bit window ladder with no data-dependent branches instead of the reference's NAF loop.
+#pragma once
+#include "constants.cuh"
+
+namespace sylow {
+
+// field dispatch by overload
+SY_HD Fp f_add(const Fp& a, const Fp& b) { return fp_add(a, b); }
+SY_HD Fp f_sub(const Fp& a, const Fp& b) { return fp_sub(a, b); }
+SY_HD Fp f_mul(const Fp& a, const Fp& b) { return fp_mul(a, b); }
+SY_HD Fp f_mul_b3(const Fp& a) { return fp_mul9(a); }  // 3b = 9
+SY_HD Fp f_neg(const Fp& a) { return fp_neg(a); }
+SY_HD bool f_is_zero(const Fp& a) { return fp_is_zero(a); }
+SY_HD void f_set_zero(Fp& a) { a = fp_zero(); }
+SY_HD void f_set_one(Fp& a) { a = fp_one(); }
+SY_HD Fp f_inv(const Fp& a) { return fp_inv(a); }
+
+SY_HD Fp2 f_add(const Fp2& a, const Fp2& b) { return fp2_add(a, b); }
+SY_HD Fp2 f_sub(const Fp2& a, const Fp2& b) { return fp2_sub(a, b); }
+SY_HD Fp2 f_mul(const Fp2& a, const Fp2& b) { return fp2_mul(a, b); }
+SY_HD Fp2 f_mul_b3(const Fp2& a) { return fp2_mul(a, SY_TAB(kTwistB3)[0]); }
+SY_HD Fp2 f_neg(const Fp2& a) { return fp2_neg(a); }
+SY_HD bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
+SY_HD void f_set_zero(Fp2& a) { a = fp2_zero(); }
+SY_HD void f_set_one(Fp2& a) { a = fp2_one(); }
+SY_HD Fp2 f_inv(const Fp2& a) { return fp2_inv(a); }
+
+template <class F>
+struct Proj {
+  F x, y, z;
+};
+template <class F>
+struct Affine {
+  F x, y;
+  bool inf;
+};
+typedef Proj<Fp> G1Proj;
+typedef Proj<Fp2> G2Proj;
+typedef Affine<Fp> G1Aff;
+typedef Affine<Fp2> G2Aff;
+
+// (0 : 1 : 0), group.rs:320-331
+template <class F>
+SY_HD Proj<F> proj_zero() {
+  Proj<F> r;
+  f_set_zero(r.x);
+  f_set_one(r.y);
+  f_set_zero(r.z);
+  return r;
+}
+
+// Alg. 9 (group.rs:339-386).  The formula maps (0:1:0) to (0:Y:0), so no select is needed for the
+// value of the affine result; the reference's select only normalises the representative.
+template <class F>
+SY_HD_NOINLINE Proj<F> proj_double(const Proj<F>& p) {
+  F t0 = f_mul(p.y, p.y);
+  F z3 = f_add(t0, t0);
+  z3 = f_add(z3, z3);
+  z3 = f_add(z3, z3);
+  F t1 = f_mul(p.y, p.z);
+  F t2 = f_mul(p.z, p.z);
+  t2 = f_mul_b3(t2);
+  F x3 = f_mul(t2, z3);
+  F y3 = f_add(t0, t2);
+  z3 = f_mul(t1, z3);
+  t1 = f_add(t2, t2);
+  t2 = f_add(t1, t2);
+  t0 = f_sub(t0, t2);
+  y3 = f_mul(t0, y3);
+  y3 = f_add(x3, y3);
+  t1 = f_mul(p.x, p.y);
+  x3 = f_mul(t0, t1);
+  x3 = f_add(x3, x3);
+  return Proj<F>{x3, y3, z3};
+}
+
+// Alg. 7 (group.rs:528-599)
+template <class F>
+SY_HD_NOINLINE Proj<F> proj_add(const Proj<F>& a, const Proj<F>& b) {
+  F t0 = f_mul(a.x, b.x);
+  F t1 = f_mul(a.y, b.y);
+  F t2 = f_mul(a.z, b.z);
+  F t3 = f_mul(f_add(a.x, a.y), f_add(b.x, b.y));
+  t3 = f_sub(t3, f_add(t0, t1));
+  F t4 = f_mul(f_add(a.y, a.z), f_add(b.y, b.z));
+  t4 = f_sub(t4, f_add(t1, t2));
+  F y3 = f_mul(f_add(a.x, a.z), f_add(b.x, b.z));
+  y3 = f_sub(y3, f_add(t0, t2));
+  F x3 = f_add(t0, t0);
+  t0 = f_add(x3, t0);
+  t2 = f_mul_b3(t2);
+  F z3 = f_add(t1, t2);
+  t1 = f_sub(t1, t2);
+  y3 = f_mul_b3(y3);
+  x3 = f_mul(t4, y3);
+  t2 = f_mul(t3, t1);
+  x3 = f_sub(t2, x3);
+  y3 = f_mul(y3, t0);
+  t1 = f_mul(t1, z3);
+  y3 = f_add(t1, y3);
+  t0 = f_mul(t0, t3);
+  z3 = f_mul(z3, t4);
+  z3 = f_add(z3, t0);
+  return Proj<F>{x3, y3, z3};
+}
+
+template <class F>
+SY_HD Proj<F> affine_to_proj(const Affine<F>& a) {
+  Proj<F> r;
+  r.x = a.x;
+  r.y = a.y;
+  if (a.inf)
+    f_set_zero(r.z);
+  else
+    f_set_one(r.z);
+  return r;
+}
+
+// group.rs:475-495: x/z, y/z; z == 0 gives (0, 1, infinity)
+template <class F>
+SY_HD_NOINLINE Affine<F> proj_to_affine(const Proj<F>& p) {
+  Affine<F> r;
+  F zi = f_inv(p.z);
+  r.inf = f_is_zero(zi);
+  r.x = f_mul(p.x, zi);
+  r.y = f_mul(p.y, zi);
+  if (r.inf) {
+    f_set_zero(r.x);
+    f_set_one(r.y);
+  }
+  return r;
+}
+
+// k * P for a 256-bit scalar k (8 LE words; the reference takes an Fp-range scalar and does not reduce
+// it mod r, group.rs:639-667 / SURVEY Q8 - the group has order r so the affine result is the same).
+// Fixed 4-bit windows, table of 0..15 multiples, complete additions: no data-dependent control flow.
+template <class F>
+SY_HD_NOINLINE Proj<F> proj_scalar_mul(const Proj<F>& p, const uint32_t* k) {
+  Proj<F> tab[16];
+  tab[0] = proj_zero<F>();
+  tab[1] = p;
+  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
+  Proj<F> acc = tab[k[7] >> 28];
+  for (int w = 62; w >= 0; w--) {
+    acc = proj_double(acc);
+    acc = proj_double(acc);
+    acc = proj_double(acc);
+    acc = proj_double(acc);
+    uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+    acc = proj_add(acc, tab[d]);
+  }
+  return acc;
+}
+
+// y^2 == x^3 + b
+SY_HD bool g1_on_curve(const Fp& x, const Fp& y) {
+  Fp rhs = fp_add(fp_mul(fp_sqr(x), x), SY_TAB(kFpThree)[0]);
+  return fp_eq(fp_sqr(y), rhs);
+}
+SY_HD bool g2_on_curve(const Fp2& x, const Fp2& y) {
+  Fp2 rhs = fp2_add(fp2_mul(fp2_sqr(x), x), SY_TAB(kTwistB)[0]);
+  return fp2_eq(fp2_sqr(y), rhs);
+}
+
+}  // namespace sylow

@@ -1,0 +1,394 @@
+// Fp arithmetic for BN254 on sm_100a: 8 x 32-bit limbs, Montgomery form (R = 2^256).
+//
+// Replaces (value-level) sylow's `Fp` operators, /root/reference/src/fields/fp.rs:304-457, which
+// delegate to crypto-bigint ConstMontyForm<U256>.  Every value that leaves the device is converted
+// back to the canonical residue in [0, p), so results are bit-identical to the reference.
+//
+// Multiplication is a CIOS Montgomery product written as PTX mad.lo.cc / madc.hi.cc carry chains
+// over two interleaved accumulators ("even" holds 64-bit columns aligned at limb 0,2,4,6 and "odd"
+// the columns aligned at limb 1,3,5,7).  ptxas fuses every mad.lo.cc/madc.hi.cc pair into ONE
+// IMAD.WIDE.U32(.X) with a predicate carry, so one Fp multiplication is 136 IMAD-pipe instructions
+// (64 for a*b, 64 for m*p, 8 for m) - the 136 "limb products" SURVEY.md 8(d) counts.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define SY_HD __host__ __device__ __forceinline__
+#define SY_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define SY_HD inline
+#define SY_HD_NOINLINE
+#endif
+// Tables live in __constant__ memory on the device.  The host copy exists only so that the
+// test-only host simulation (tests/hostsim, -DSYLOW_HOSTSIM) can run the same tower/pairing source
+// on a CPU; the product library never executes it.
+#if defined(__CUDA_ARCH__)
+#define SY_TAB(name) name##_d
+#else
+#define SY_TAB(name) name##_h
+#endif
+#define SY_DEFINE_TABLE(type, name, n, ...)                       \
+  __device__ __constant__ const type name##_d[n] = {__VA_ARGS__}; \
+  static const type name##_h[n] = {__VA_ARGS__};
+
+namespace sylow {
+
+struct Fp {
+  uint32_t l[8];
+};
+
+// p = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47 (fp.rs:51-56)
+#define SY_P0 0xd87cfd47
+#define SY_P1 0x3c208c16
+#define SY_P2 0x6871ca8d
+#define SY_P3 0x97816a91
+#define SY_P4 0x8181585d
+#define SY_P5 0xb85045b6
+#define SY_P6 0xe131a029
+#define SY_P7 0x30644e72
+#define SY_STR2(x) #x
+#define SY_STR(x) SY_STR2(x)
+#define SY_INV 0xe4866389u  // -p^{-1} mod 2^32
+
+SY_DEFINE_TABLE(uint32_t, kP, 8, SY_P0, SY_P1, SY_P2, SY_P3, SY_P4, SY_P5, SY_P6, SY_P7)
+
+SY_HD Fp fp_zero() {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = 0;
+  return r;
+}
+// R mod p  (Montgomery form of 1)
+SY_HD Fp fp_one() {
+  return Fp{{0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}};
+}
+// R^2 mod p (to-Montgomery multiplier) and R^3 mod p (for 2^256 * hi in hash_to_field)
+SY_HD Fp fp_R2() {
+  return Fp{{0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u}};
+}
+SY_HD Fp fp_R3() {
+  return Fp{{0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u}};
+}
+
+SY_HD bool fp_is_zero(const Fp& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.l[i];
+  return o == 0;
+}
+SY_HD bool fp_eq(const Fp& a, const Fp& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) o |= a.l[i] ^ b.l[i];
+  return o == 0;
+}
+SY_HD Fp fp_select(bool c, const Fp& a, const Fp& b) {  // c ? a : b
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+  return r;
+}
+
+// r = a - p if a >= p else a      (a < 2p)
+SY_HD void fp_final_sub(uint32_t* a) {
+  uint32_t t[8], borrow;
+#if !defined(__CUDA_ARCH__)
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    int64_t d = (int64_t)a[i] - (int64_t)SY_TAB(kP)[i] + bw;
+    t[i] = (uint32_t)d;
+    bw = d >> 32;
+  }
+  borrow = (uint32_t)bw;
+#else
+  asm("sub.cc.u32 %0, %9, " SY_STR(SY_P0) ";\n\t"
+      "subc.cc.u32 %1, %10, " SY_STR(SY_P1) ";\n\t"
+      "subc.cc.u32 %2, %11, " SY_STR(SY_P2) ";\n\t"
+      "subc.cc.u32 %3, %12, " SY_STR(SY_P3) ";\n\t"
+      "subc.cc.u32 %4, %13, " SY_STR(SY_P4) ";\n\t"
+      "subc.cc.u32 %5, %14, " SY_STR(SY_P5) ";\n\t"
+      "subc.cc.u32 %6, %15, " SY_STR(SY_P6) ";\n\t"
+      "subc.cc.u32 %7, %16, " SY_STR(SY_P7) ";\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#endif
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : t[i];
+}
+
+SY_HD Fp fp_add(const Fp& a, const Fp& b) {
+  Fp r;
+#if !defined(__CUDA_ARCH__)
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] + b.l[i];
+    r.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#else
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#endif
+  fp_final_sub(r.l);  // a + b < 2p < 2^255: no carry out of limb 7
+  return r;
+}
+
+SY_HD Fp fp_sub(const Fp& a, const Fp& b) {
+  Fp r;
+  uint32_t borrow;
+#if !defined(__CUDA_ARCH__)
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    int64_t d = (int64_t)a.l[i] - (int64_t)b.l[i] + bw;
+    r.l[i] = (uint32_t)d;
+    bw = d >> 32;
+  }
+  borrow = (uint32_t)bw;
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)r.l[i] + (borrow & SY_TAB(kP)[i]);
+    r.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#else
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]),
+        "=r"(borrow)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  // borrow is 0 or 0xffffffff: add back p & borrow
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;"
+      : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+      : "r"(borrow & SY_P0), "r"(borrow & SY_P1), "r"(borrow & SY_P2), "r"(borrow & SY_P3), "r"(borrow & SY_P4),
+        "r"(borrow & SY_P5), "r"(borrow & SY_P6), "r"(borrow & SY_P7));
+#endif
+  return r;
+}
+
+// a / 2 mod p: (a + (a odd ? p : 0)) >> 1.  Works on the Montgomery representative directly.
+SY_HD Fp fp_halve(const Fp& a) {
+  uint32_t m = 0u - (a.l[0] & 1u);
+  Fp t;
+#if !defined(__CUDA_ARCH__)
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a.l[i] + (m & SY_TAB(kP)[i]);
+    t.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#else
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7])
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(m & SY_P0), "r"(m & SY_P1), "r"(m & SY_P2), "r"(m & SY_P3), "r"(m & SY_P4), "r"(m & SY_P5), "r"(m & SY_P6), "r"(m & SY_P7));
+#endif
+  Fp r;  // a + p < 2^255: the sum fits in 8 limbs
+#pragma unroll
+  for (int i = 0; i < 7; i++) r.l[i] = (t.l[i] >> 1) | (t.l[i + 1] << 31);
+  r.l[7] = t.l[7] >> 1;
+  return r;
+}
+
+SY_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
+SY_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
+
+// ---- Montgomery multiplication ------------------------------------------------------------------
+// One CIOS round for multiplier limb bi.  T = X + Y * 2^32 (X: columns at limbs 0,2,4,6; Y: columns at
+// limbs 1,3,5,7).  After the round X[0] == 0 and the caller swaps the roles of X and Y, which divides
+// T by 2^32.  Bounds: T < 2p on entry, T + a*bi + m*p < 2^287, so neither accumulator overflows.
+#if defined(__CUDA_ARCH__)
+template <bool FIRST>
+__device__ __forceinline__ void mont_round(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+  if (FIRST) {
+    asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
+        : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+    asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
+        : "=r"(Y[0]), "=r"(Y[1]), "=r"(Y[2]), "=r"(Y[3]), "=r"(Y[4]), "=r"(Y[5]), "=r"(Y[6]), "=r"(Y[7])
+        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+  } else {
+    // X[0] += Y[1]; Y = (Y >> 64) + a_odd * bi   (carry of the first add feeds the chain)
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %9, %13, %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, %13, %4;\n\t"
+        "madc.lo.cc.u32 %3, %10, %13, %5;\n\t"
+        "madc.hi.cc.u32 %4, %10, %13, %6;\n\t"
+        "madc.lo.cc.u32 %5, %11, %13, %7;\n\t"
+        "madc.hi.cc.u32 %6, %11, %13, %8;\n\t"
+        "madc.lo.cc.u32 %7, %12, %13, 0;\n\t"
+        "madc.hi.u32 %8, %12, %13, 0;"
+        : "+r"(X[0]), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7])
+        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+    // X += a_even * bi; carry out (weight 2^256) lands in Y[7]
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+  }
+  uint32_t m = X[0] * SY_INV;
+  // Y += m * p_odd   (no carry out: Y * 2^32 <= T < 2^287)
+  asm("mad.lo.cc.u32 %0, %8, " SY_STR(SY_P1) ", %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, " SY_STR(SY_P1) ", %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, " SY_STR(SY_P3) ", %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, " SY_STR(SY_P3) ", %3;\n\t"
+      "madc.lo.cc.u32 %4, %8, " SY_STR(SY_P5) ", %4;\n\t"
+      "madc.hi.cc.u32 %5, %8, " SY_STR(SY_P5) ", %5;\n\t"
+      "madc.lo.cc.u32 %6, %8, " SY_STR(SY_P7) ", %6;\n\t"
+      "madc.hi.u32 %7, %8, " SY_STR(SY_P7) ", %7;"
+      : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7])
+      : "r"(m));
+  // X += m * p_even; carry out lands in Y[7]; X[0] becomes 0
+  asm("mad.lo.cc.u32 %0, %9, " SY_STR(SY_P0) ", %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, " SY_STR(SY_P0) ", %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, " SY_STR(SY_P2) ", %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, " SY_STR(SY_P2) ", %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, " SY_STR(SY_P4) ", %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, " SY_STR(SY_P4) ", %5;\n\t"
+      "madc.lo.cc.u32 %6, %9, " SY_STR(SY_P6) ", %6;\n\t"
+      "madc.hi.cc.u32 %7, %9, " SY_STR(SY_P6) ", %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7])
+      : "r"(m));
+}
+
+// r = a * b / R mod p, fully reduced.  Requires a * b < p * R (true for a, b < p and for the
+// to-Montgomery use a < 2^256, b = R^2 mod p).
+__device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) {
+  uint32_t ev[8], od[8];
+  mont_round<true>(ev, od, a.l, b.l[0]);
+  mont_round<false>(od, ev, a.l, b.l[1]);
+  mont_round<false>(ev, od, a.l, b.l[2]);
+  mont_round<false>(od, ev, a.l, b.l[3]);
+  mont_round<false>(ev, od, a.l, b.l[4]);
+  mont_round<false>(od, ev, a.l, b.l[5]);
+  mont_round<false>(ev, od, a.l, b.l[6]);
+  mont_round<false>(od, ev, a.l, b.l[7]);
+  // last round used X = od, Y = ev: result = ev + (od >> 32)
+  Fp r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+      : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+  fp_final_sub(r.l);
+  return r;
+}
+#else
+// host simulation only (tests/hostsim): textbook CIOS with 64-bit temporaries
+inline Fp fp_mul(const Fp& a, const Fp& b) {
+  uint32_t t[10] = {0};
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)a.l[j] * b.l[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[8] = (uint32_t)c;
+    t[9] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * SY_INV;
+    c = (uint64_t)m * kP_h[0] + t[0];
+    c >>= 32;
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)m * kP_h[j] + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[7] = (uint32_t)c;
+    t[8] = t[9] + (uint32_t)(c >> 32);
+  }
+  Fp r;
+  for (int i = 0; i < 8; i++) r.l[i] = t[i];
+  fp_final_sub(r.l);
+  return r;
+}
+#endif
+
+SY_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
+
+SY_HD Fp fp_to_mont(const Fp& a) { return fp_mul(a, fp_R2()); }
+SY_HD Fp fp_from_mont(const Fp& a) {
+  Fp one = fp_zero();
+  one.l[0] = 1;
+  return fp_mul(a, one);
+}
+
+// small-constant helpers (additions only)
+SY_HD Fp fp_mul3(const Fp& a) { return fp_add(fp_dbl(a), a); }
+SY_HD Fp fp_mul9(const Fp& a) {
+  Fp t = fp_dbl(fp_dbl(fp_dbl(a)));
+  return fp_add(t, a);
+}
+
+// a^e for a fixed 256-bit exponent given as 8 LE words (uniform across the warp)
+SY_HD_NOINLINE Fp fp_pow(const Fp& a, const uint32_t* e, int top_bit) {
+  Fp r = a;
+  for (int i = top_bit - 1; i >= 0; i--) {
+    r = fp_sqr(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) r = fp_mul(r, a);
+  }
+  return r;
+}
+
+// p-2, (p-1)/2, (p+1)/4 as LE words
+SY_DEFINE_TABLE(uint32_t, kPm2, 8, 0xd87cfd45, 0x3c208c16, 0x6871ca8d, 0x97816a91, 0x8181585d, 0xb85045b6, 0xe131a029, 0x30644e72)
+SY_DEFINE_TABLE(uint32_t, kPm1h, 8, 0x6c3e7ea3, 0x9e10460b, 0xb438e546, 0xcbc0b548, 0x40c0ac2e, 0xdc2822db, 0x7098d014, 0x18322739)
+SY_DEFINE_TABLE(uint32_t, kPp1q, 8, 0xb61f3f52, 0x4f082305, 0x5a1c72a3, 0x65e05aa4, 0xa0605617, 0x6e14116d, 0xb84c680a, 0x0c19139c)
+
+// inv(0) = 0 like the reference (fp.rs:418-424)
+SY_HD Fp fp_inv(const Fp& a) { return fp_pow(a, SY_TAB(kPm2), 253); }
+
+}  // namespace sylow

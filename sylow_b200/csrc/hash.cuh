@@ -1,0 +1,186 @@
+// RFC 9380 hash-to-curve for BN254 G1 as sylow does it: expand_message_xmd over Keccak-256,
+// hash_to_field (count 2, L 48), two Shallue-van de Woestijne maps and one projective addition.
+//
+// Replaces /root/reference/src/hasher.rs:84-128 (hash_to_field), :201-250 (XMD expand_message),
+// /root/reference/src/svdw.rs:180-262 (unchecked_map_to_point) and
+// /root/reference/src/groups/g1.rs:307-331 (hash_to_curve).  The digest is legacy Keccak-256
+// (pad 0x01), i.e. sha3::Keccak256 as used by src/lib.rs:181,225.
+#pragma once
+#include "curve.cuh"
+
+namespace sylow {
+
+SY_DEFINE_TABLE(uint64_t, kKeccakRC, 24, 0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808Aull,
+                0x8000000080008000ull, 0x000000000000808Bull, 0x0000000080000001ull, 0x8000000080008081ull,
+                0x8000000000008009ull, 0x000000000000008Aull, 0x0000000000000088ull, 0x0000000080008009ull,
+                0x000000008000000Aull, 0x000000008000808Bull, 0x800000000000008Bull, 0x8000000000008089ull,
+                0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800Aull,
+                0x800000008000000Aull, 0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull,
+                0x8000000080008008ull)
+
+SY_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+
+// Keccak-f[1600], lanes s[x + 5y] (FIPS 202 section 3.2)
+SY_HD_NOINLINE void keccak_f1600(uint64_t* st) {
+  uint64_t s[25];
+#pragma unroll
+  for (int i = 0; i < 25; i++) s[i] = st[i];
+  for (int round = 0; round < 24; round++) {
+    uint64_t c[5], d[5];
+#pragma unroll
+    for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+#pragma unroll
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+    for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
+    // rho + pi
+    uint64_t b[25];
+    b[0] = s[0];
+    b[10] = rotl64(s[1], 1);
+    b[20] = rotl64(s[2], 62);
+    b[5] = rotl64(s[3], 28);
+    b[15] = rotl64(s[4], 27);
+    b[16] = rotl64(s[5], 36);
+    b[1] = rotl64(s[6], 44);
+    b[11] = rotl64(s[7], 6);
+    b[21] = rotl64(s[8], 55);
+    b[6] = rotl64(s[9], 20);
+    b[7] = rotl64(s[10], 3);
+    b[17] = rotl64(s[11], 10);
+    b[2] = rotl64(s[12], 43);
+    b[12] = rotl64(s[13], 25);
+    b[22] = rotl64(s[14], 39);
+    b[23] = rotl64(s[15], 41);
+    b[8] = rotl64(s[16], 45);
+    b[18] = rotl64(s[17], 15);
+    b[3] = rotl64(s[18], 21);
+    b[13] = rotl64(s[19], 8);
+    b[14] = rotl64(s[20], 18);
+    b[24] = rotl64(s[21], 2);
+    b[9] = rotl64(s[22], 61);
+    b[19] = rotl64(s[23], 56);
+    b[4] = rotl64(s[24], 14);
+#pragma unroll
+    for (int y = 0; y < 25; y += 5)
+#pragma unroll
+      for (int x = 0; x < 5; x++) s[y + x] = b[y + x] ^ ((~b[y + (x + 1) % 5]) & b[y + (x + 2) % 5]);
+    s[0] ^= SY_TAB(kKeccakRC)[round];
+  }
+#pragma unroll
+  for (int i = 0; i < 25; i++) st[i] = s[i];
+}
+
+struct Keccak256 {
+  uint64_t s[25];
+  int pos;
+};
+SY_HD void keccak_init(Keccak256& k) {
+  for (int i = 0; i < 25; i++) k.s[i] = 0;
+  k.pos = 0;
+}
+SY_HD void keccak_absorb_byte(Keccak256& k, uint8_t b) {
+  k.s[k.pos >> 3] ^= (uint64_t)b << ((k.pos & 7) * 8);
+  if (++k.pos == 136) {
+    keccak_f1600(k.s);
+    k.pos = 0;
+  }
+}
+SY_HD void keccak_absorb(Keccak256& k, const uint8_t* p, size_t n) {
+  for (size_t i = 0; i < n; i++) keccak_absorb_byte(k, p[i]);
+}
+SY_HD void keccak_final(Keccak256& k, uint8_t* out32) {
+  k.s[k.pos >> 3] ^= (uint64_t)0x01 << ((k.pos & 7) * 8);
+  k.s[16] ^= 0x8000000000000000ull;  // byte 135
+  keccak_f1600(k.s);
+  for (int i = 0; i < 32; i++) out32[i] = (uint8_t)(k.s[i >> 3] >> ((i & 7) * 8));
+}
+
+// 48 big-endian bytes -> value mod p, in Montgomery form (hasher.rs:93-111)
+SY_HD Fp fp_from_be48_mod(const uint8_t* b) {
+  Fp hi = fp_zero(), lo;
+  for (int i = 0; i < 4; i++) {  // bytes 0..15 -> 128-bit hi
+    const uint8_t* q = b + 12 - 4 * i;
+    hi.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+  }
+  for (int i = 0; i < 8; i++) {  // bytes 16..47 -> 256-bit lo
+    const uint8_t* q = b + 44 - 4 * i;
+    lo.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+  }
+  // lo * R + hi * 2^256 * R  (mod p)
+  return fp_add(fp_mul(lo, fp_R2()), fp_mul(hi, fp_R3()));
+}
+
+// expand_message_xmd(msg, DST, 96) with Keccak-256, then two field elements.
+// dst_prime = DST || I2OSP(len(DST), 1), already assembled by the caller (<= 256 bytes).
+SY_HD_NOINLINE void hash_to_field_keccak(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime,
+                                         size_t dst_prime_len, Fp& u0, Fp& u1) {
+  Keccak256 k;
+  uint8_t b0[32], bi[32], uni[96];
+  keccak_init(k);
+  for (int i = 0; i < 136; i++) keccak_absorb_byte(k, 0);  // Z_pad = block size of Keccak-256
+  keccak_absorb(k, msg, msg_len);
+  keccak_absorb_byte(k, 0);
+  keccak_absorb_byte(k, 96);  // I2OSP(len_in_bytes = 96, 2)
+  keccak_absorb_byte(k, 0);   // I2OSP(0, 1)
+  keccak_absorb(k, dst_prime, dst_prime_len);
+  keccak_final(k, b0);
+  for (int i = 0; i < 32; i++) bi[i] = 0;
+  for (int blk = 1; blk <= 3; blk++) {
+    keccak_init(k);
+    for (int i = 0; i < 32; i++) keccak_absorb_byte(k, b0[i] ^ bi[i]);  // b_0 xor b_{i-1} (b_0 alone for i = 1)
+    keccak_absorb_byte(k, (uint8_t)blk);
+    keccak_absorb(k, dst_prime, dst_prime_len);
+    keccak_final(k, bi);
+    for (int i = 0; i < 32; i++) uni[32 * (blk - 1) + i] = bi[i];
+  }
+  u0 = fp_from_be48_mod(uni);
+  u1 = fp_from_be48_mod(uni + 48);
+}
+
+SY_HD bool fp_is_square(const Fp& a) {  // fp.rs:625-631 (true for 0)
+  Fp l = fp_pow(a, SY_TAB(kPm1h), 252);
+  return fp_is_zero(l) | fp_eq(l, fp_one());
+}
+SY_HD uint32_t fp_sgn0(const Fp& a) { return fp_from_mont(a).l[0] & 1u; }  // fp.rs:636-644
+
+SY_HD Fp svdw_g(const Fp& x) { return fp_add(fp_mul(fp_sqr(x), x), SY_TAB(kFpThree)[0]); }  // x^3 + 3 (a = 0)
+
+// svdw.rs:180-262.  Returns false if the final sqrt check fails (MapError::SvdWError).
+SY_HD_NOINLINE bool svdw_map_to_point(const Fp& u, Fp& x, Fp& y) {
+  const Fp one = fp_one();
+  Fp tv1 = fp_mul(fp_sqr(u), SY_TAB(kSvdwC1)[0]);
+  Fp tv2 = fp_add(one, tv1);
+  tv1 = fp_sub(one, tv1);
+  Fp tv3 = fp_inv(fp_mul(tv1, tv2));
+  Fp tv4 = fp_mul(fp_mul(fp_mul(u, tv1), tv3), SY_TAB(kSvdwC3)[0]);
+  Fp x1 = fp_sub(SY_TAB(kSvdwC2)[0], tv4);
+  bool e1 = fp_is_square(svdw_g(x1));
+  Fp x2 = fp_add(SY_TAB(kSvdwC2)[0], tv4);
+  bool e2 = fp_is_square(svdw_g(x2)) & !e1;
+  Fp x3 = fp_mul(fp_sqr(tv2), tv3);
+  x3 = fp_add(fp_mul(fp_sqr(x3), SY_TAB(kSvdwC4)[0]), SY_TAB(kSvdwZ)[0]);
+  x = fp_select(e1, x1, x3);
+  x = fp_select(e2, x2, x);
+  Fp gx = svdw_g(x);
+  y = fp_pow(gx, SY_TAB(kPp1q), 251);  // fp.rs:611-616
+  bool ok = fp_eq(fp_sqr(y), gx);
+  bool e3 = fp_sgn0(u) == fp_sgn0(y);
+  y = fp_select(e3, y, fp_neg(y));
+  return ok;
+}
+
+// g1.rs:307-331: map both field elements and add (projective result)
+SY_HD_NOINLINE bool hash_to_g1(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len,
+                               G1Proj& out) {
+  Fp u0, u1;
+  hash_to_field_keccak(msg, msg_len, dst_prime, dst_prime_len, u0, u1);
+  G1Proj a, b;
+  bool ok = svdw_map_to_point(u0, a.x, a.y);
+  ok &= svdw_map_to_point(u1, b.x, b.y);
+  a.z = fp_one();
+  b.z = fp_one();
+  out = proj_add(a, b);
+  return ok;
+}
+
+}  // namespace sylow

@@ -1,0 +1,164 @@
+// Optimal-ate pairing on BN254: fused Miller loop and final exponentiation.
+//
+// Replaces /root/reference/src/pairing.rs: G2Affine::precompute (:676-708) composed with
+// G2PreComputed::miller_loop (:590-619) as ONE pass (no 16.7 KB coefficient table round trip), the
+// Costello-Lange-Naehrig doubling/addition steps (:756-818) with exactly the reference's line
+// scalings so the MillerLoopResult itself is bit-identical, and
+// MillerLoopResult::final_exponentiation (:245-492).
+#pragma once
+#include "curve.cuh"
+
+namespace sylow {
+
+struct Ell {
+  Fp2 c0, c1, c2;
+};
+
+// pairing.rs:798-818.  Mutates R, returns the line triple.
+SY_HD_NOINLINE Ell g2_doubling_step(G2Proj& r) {
+  Fp2 a = fp2_halve(fp2_mul(r.x, r.y));
+  Fp2 b = fp2_sqr(r.y);
+  Fp2 c = fp2_sqr(r.z);
+  Fp2 d = fp2_mul3(c);
+  Fp2 e = fp2_mul(SY_TAB(kTwistB)[0], d);
+  Fp2 f = fp2_mul3(e);
+  Fp2 g = fp2_halve(fp2_add(b, f));
+  Fp2 h = fp2_sub(fp2_sqr(fp2_add(r.y, r.z)), fp2_add(b, c));
+  Fp2 i = fp2_sub(e, b);
+  Fp2 j = fp2_sqr(r.x);
+  Fp2 e_sq = fp2_sqr(e);
+  r.x = fp2_mul(a, fp2_sub(b, f));
+  r.y = fp2_sub(fp2_sqr(g), fp2_mul3(e_sq));
+  r.z = fp2_mul(b, h);
+  return Ell{fp2_mul_xi(i), fp2_neg(h), fp2_mul3(j)};
+}
+
+// pairing.rs:756-772
+SY_HD_NOINLINE Ell g2_addition_step(G2Proj& r, const Fp2& qx, const Fp2& qy) {
+  Fp2 d = fp2_sub(r.x, fp2_mul(r.z, qx));
+  Fp2 e = fp2_sub(r.y, fp2_mul(r.z, qy));
+  Fp2 f = fp2_sqr(d);
+  Fp2 g = fp2_sqr(e);
+  Fp2 h = fp2_mul(d, f);
+  Fp2 i = fp2_mul(r.x, f);
+  Fp2 j = fp2_sub(fp2_add(fp2_mul(r.z, g), h), fp2_dbl(i));
+  Fp2 ry = fp2_sub(fp2_mul(e, fp2_sub(i, j)), fp2_mul(h, r.y));
+  r.x = fp2_mul(d, j);
+  r.y = ry;
+  r.z = fp2_mul(r.z, h);
+  return Ell{fp2_mul_xi(fp2_sub(fp2_mul(e, qx), fp2_mul(d, qy))), d, fp2_neg(e)};
+}
+
+// f <- f * l(P),  l(P) = (c0, c1 * yP, c2 * xP)   (pairing.rs:597)
+SY_HD Fp12 miller_mul_line(const Fp12& f, const Ell& l, const Fp& xp, const Fp& yp) {
+  Fp2 lvw = fp2_mul_fp(l.c1, yp);
+  Fp2 lvv = fp2_mul_fp(l.c2, xp);
+  return fp12_sparse_mul(f, l.c0, lvw, lvv);
+}
+
+// Fused precompute + miller_loop for one (P, Q) pair of finite affine points.
+SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const Fp2& qy) {
+  G2Proj r{qx, qy, fp2_one()};
+  Fp2 nqy = fp2_neg(qy);
+  Fp12 f = fp12_one();
+  for (int i = 0; i < 64; i++) {
+    Ell l = g2_doubling_step(r);
+    if (i != 0) f = fp12_sqr(f);  // 1^2 = 1
+    f = miller_mul_line(f, l, xp, yp);
+    int digit = SY_TAB(kAteNaf)[i];
+    if (digit != 0) {
+      l = g2_addition_step(r, qx, digit > 0 ? qy : nqy);
+      f = miller_mul_line(f, l, xp, yp);
+    }
+  }
+  // Q1 = psi(Q), Q2 = -psi(Q1)   (pairing.rs:701-706, g2.rs:140-152)
+  Fp2 q1x = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(qx));
+  Fp2 q1y = fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(qy));
+  Fp2 q2x = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q1x));
+  Fp2 q2y = fp2_neg(fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q1y)));
+  Ell l = g2_addition_step(r, q1x, q1y);
+  f = miller_mul_line(f, l, xp, yp);
+  l = g2_addition_step(r, q2x, q2y);
+  f = miller_mul_line(f, l, xp, yp);
+  return f;
+}
+
+// ---------------------------------------------------------------------------- final exponentiation
+// fp6.rs:203-209 / fp12.rs:515-522 for e in {1, 2, 3}
+SY_HD_NOINLINE Fp12 fp12_frobenius(const Fp12& a, int e) {
+  bool odd = e & 1;
+  Fp12 r;
+  const Fp2 c61 = SY_TAB(kFrob6C1)[e], c62 = SY_TAB(kFrob6C2)[e], c12 = SY_TAB(kFrob12C1)[e];
+  r.c0.c0 = odd ? fp2_conj(a.c0.c0) : a.c0.c0;
+  r.c0.c1 = fp2_mul(odd ? fp2_conj(a.c0.c1) : a.c0.c1, c61);
+  r.c0.c2 = fp2_mul(odd ? fp2_conj(a.c0.c2) : a.c0.c2, c62);
+  r.c1.c0 = fp2_mul(odd ? fp2_conj(a.c1.c0) : a.c1.c0, c12);
+  r.c1.c1 = fp2_mul(fp2_mul(odd ? fp2_conj(a.c1.c1) : a.c1.c1, c61), c12);
+  r.c1.c2 = fp2_mul(fp2_mul(odd ? fp2_conj(a.c1.c2) : a.c1.c2, c62), c12);
+  return r;
+}
+
+// pairing.rs:274-289
+SY_HD void fp4_square(const Fp2& a, const Fp2& b, Fp2& c0, Fp2& c1) {
+  Fp2 t0 = fp2_sqr(a);
+  Fp2 t1 = fp2_sqr(b);
+  c0 = fp2_add(fp2_mul_xi(t1), t0);
+  c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
+}
+
+// Granger-Scott (pairing.rs:309-346)
+SY_HD_NOINLINE Fp12 cyclotomic_squared(const Fp12& f) {
+  Fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
+  Fp2 t0, t1, t2, t3;
+  fp4_square(z0, z1, t0, t1);
+  z0 = fp2_sub(t0, z0);
+  z0 = fp2_add(fp2_dbl(z0), t0);
+  z1 = fp2_add(t1, z1);
+  z1 = fp2_add(fp2_dbl(z1), t1);
+  fp4_square(z2, z3, t0, t1);
+  fp4_square(z4, z5, t2, t3);
+  z4 = fp2_sub(t0, z4);
+  z4 = fp2_add(fp2_dbl(z4), t0);
+  z5 = fp2_add(t1, z5);
+  z5 = fp2_add(fp2_dbl(z5), t1);
+  t0 = fp2_mul_xi(t3);
+  z2 = fp2_add(t0, z2);
+  z2 = fp2_add(fp2_dbl(z2), t0);
+  z3 = fp2_sub(t2, z3);
+  z3 = fp2_add(fp2_dbl(z3), t2);
+  return Fp12{Fp6{z0, z4, z3}, Fp6{z2, z1, z5}};
+}
+
+// conj(f^x) with x = BLS_X (pairing.rs:366-392).  The reference walks 256 exponent bits; the
+// leading zero bits only square 1, so starting at bit 62 is exact.
+SY_HD_NOINLINE Fp12 exp_by_neg_z(const Fp12& f) {
+  Fp12 res = f;
+  for (int i = 61; i >= 0; i--) {
+    res = cyclotomic_squared(res);
+    if ((SY_BLS_X >> i) & 1) res = fp12_mul(res, f);
+  }
+  return fp12_conj(res);
+}
+
+// pairing.rs:245-492
+SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
+  // easy part (:410-415)
+  Fp12 f = fp12_mul(fp12_conj(f0), fp12_inv(f0));
+  Fp12 inp = fp12_mul(fp12_frobenius(f, 2), f);
+  // hard part (:437-489)
+  Fp12 a = exp_by_neg_z(inp);
+  Fp12 b = cyclotomic_squared(a);
+  Fp12 c = cyclotomic_squared(b);
+  Fp12 d = fp12_mul(c, b);
+  Fp12 e = exp_by_neg_z(d);
+  Fp12 g = exp_by_neg_z(cyclotomic_squared(e));
+  Fp12 k = fp12_mul(fp12_mul(fp12_conj(g), e), fp12_conj(d));
+  Fp12 l = fp12_mul(k, b);
+  Fp12 n = fp12_mul(inp, fp12_mul(k, e));
+  Fp12 p = fp12_mul(fp12_frobenius(l, 1), n);
+  Fp12 r = fp12_mul(fp12_frobenius(k, 2), p);
+  Fp12 u = fp12_frobenius(fp12_mul(fp12_conj(inp), l), 3);
+  return fp12_mul(u, r);
+}
+
+}  // namespace sylow

@@ -1,0 +1,199 @@
+// Tower Fp2 -> Fp6 -> Fp12 for BN254 (u^2 = -1, v^3 = xi = 9+u, w^2 = v), Montgomery-form limbs.
+//
+// Value-level replacement of /root/reference/src/fields/{extensions,fp2,fp6,fp12}.rs.  The reference
+// uses schoolbook Fp2/Fp6 products "for constant time"; field arithmetic is exact, so Karatsuba forms
+// give bit-identical values with fewer limb products.
+#pragma once
+#include "fp.cuh"
+
+namespace sylow {
+
+struct Fp2 {
+  Fp c0, c1;
+};
+struct Fp6 {
+  Fp2 c0, c1, c2;
+};
+struct Fp12 {
+  Fp6 c0, c1;
+};
+
+// ------------------------------------------------------------------------------------------ Fp2
+SY_HD Fp2 fp2_zero() { return Fp2{fp_zero(), fp_zero()}; }
+SY_HD Fp2 fp2_one() { return Fp2{fp_one(), fp_zero()}; }
+SY_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
+SY_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
+SY_HD Fp2 fp2_add(const Fp2& a, const Fp2& b) { return Fp2{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+SY_HD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return Fp2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+SY_HD Fp2 fp2_dbl(const Fp2& a) { return Fp2{fp_dbl(a.c0), fp_dbl(a.c1)}; }
+SY_HD Fp2 fp2_neg(const Fp2& a) { return Fp2{fp_neg(a.c0), fp_neg(a.c1)}; }
+SY_HD Fp2 fp2_mul3(const Fp2& a) { return fp2_add(fp2_dbl(a), a); }
+// frobenius(1): the Fp non-residue is -1, so this is conjugation (fp2.rs:119-133)
+SY_HD Fp2 fp2_conj(const Fp2& a) { return Fp2{a.c0, fp_neg(a.c1)}; }
+SY_HD Fp2 fp2_select(bool c, const Fp2& a, const Fp2& b) {
+  return Fp2{fp_select(c, a.c0, b.c0), fp_select(c, a.c1, b.c1)};
+}
+// scale(1/2) (pairing.rs:799,805): halving the Montgomery representative halves the value
+SY_HD Fp2 fp2_halve(const Fp2& a) { return Fp2{fp_halve(a.c0), fp_halve(a.c1)}; }
+
+// (a0 + a1 u)(9 + u) = (9 a0 - a1) + (a0 + 9 a1) u    (fp2.rs:99-107)
+SY_HD Fp2 fp2_mul_xi(const Fp2& a) {
+  Fp t0 = fp_mul9(a.c0), t1 = fp_mul9(a.c1);
+  return Fp2{fp_sub(t0, a.c1), fp_add(t1, a.c0)};
+}
+
+// Karatsuba: 3 Fp products (value-equal to the schoolbook of fp2.rs:302-305)
+SY_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+  Fp t0 = fp_mul(a.c0, b.c0);
+  Fp t1 = fp_mul(a.c1, b.c1);
+  Fp s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+  return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(s, t0), t1)};
+}
+
+// fp2.rs:164-171
+SY_HD_NOINLINE Fp2 fp2_sqr(const Fp2& a) {
+  Fp t = fp_mul(a.c0, a.c1);
+  Fp s = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+  return Fp2{s, fp_dbl(t)};
+}
+
+// FieldExtension::scale by a base-field element (extensions.rs:86-94)
+SY_HD_NOINLINE Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return Fp2{fp_mul(a.c0, k), fp_mul(a.c1, k)}; }
+
+// fp2.rs:343-361
+SY_HD_NOINLINE Fp2 fp2_inv(const Fp2& a) {
+  Fp t = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+  return Fp2{fp_mul(a.c0, t), fp_neg(fp_mul(a.c1, t))};
+}
+
+// ------------------------------------------------------------------------------------------ Fp6
+SY_HD Fp6 fp6_zero() { return Fp6{fp2_zero(), fp2_zero(), fp2_zero()}; }
+SY_HD Fp6 fp6_one() { return Fp6{fp2_one(), fp2_zero(), fp2_zero()}; }
+SY_HD Fp6 fp6_add(const Fp6& a, const Fp6& b) {
+  return Fp6{fp2_add(a.c0, b.c0), fp2_add(a.c1, b.c1), fp2_add(a.c2, b.c2)};
+}
+SY_HD Fp6 fp6_sub(const Fp6& a, const Fp6& b) {
+  return Fp6{fp2_sub(a.c0, b.c0), fp2_sub(a.c1, b.c1), fp2_sub(a.c2, b.c2)};
+}
+SY_HD Fp6 fp6_neg(const Fp6& a) { return Fp6{fp2_neg(a.c0), fp2_neg(a.c1), fp2_neg(a.c2)}; }
+SY_HD Fp6 fp6_dbl(const Fp6& a) { return Fp6{fp2_dbl(a.c0), fp2_dbl(a.c1), fp2_dbl(a.c2)}; }
+// multiplication by v (fp6.rs:189-191)
+SY_HD Fp6 fp6_mul_v(const Fp6& a) { return Fp6{fp2_mul_xi(a.c2), a.c0, a.c1}; }
+SY_HD bool fp6_eq(const Fp6& a, const Fp6& b) { return fp2_eq(a.c0, b.c0) & fp2_eq(a.c1, b.c1) & fp2_eq(a.c2, b.c2); }
+
+// Karatsuba, 6 Fp2 products (value-equal to the 36-product schoolbook of fp6.rs:267-368; this is
+// the form the reference quotes in its own comment at fp6.rs:274-283)
+SY_HD_NOINLINE Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
+  Fp2 t0 = fp2_mul(a.c0, b.c0);
+  Fp2 t1 = fp2_mul(a.c1, b.c1);
+  Fp2 t2 = fp2_mul(a.c2, b.c2);
+  Fp2 r0 = fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2));
+  r0 = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(r0, t1), t2)), t0);
+  Fp2 r1 = fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1));
+  r1 = fp2_add(fp2_sub(fp2_sub(r1, t0), t1), fp2_mul_xi(t2));
+  Fp2 r2 = fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2));
+  r2 = fp2_sub(fp2_add(fp2_sub(r2, t0), t1), t2);
+  return Fp6{r0, r1, r2};
+}
+
+// CH-SQR (fp6.rs:219-236)
+SY_HD_NOINLINE Fp6 fp6_sqr(const Fp6& a) {
+  Fp2 t0 = fp2_sqr(a.c0);
+  Fp2 t1 = fp2_dbl(fp2_mul(a.c0, a.c1));
+  Fp2 t2 = fp2_sqr(fp2_add(fp2_sub(a.c0, a.c1), a.c2));
+  Fp2 s3 = fp2_dbl(fp2_mul(a.c1, a.c2));
+  Fp2 s4 = fp2_sqr(a.c2);
+  Fp6 r;
+  r.c0 = fp2_add(t0, fp2_mul_xi(s3));
+  r.c1 = fp2_add(t1, fp2_mul_xi(s4));
+  r.c2 = fp2_sub(fp2_sub(fp2_add(fp2_add(t1, t2), s3), t0), s4);
+  return r;
+}
+
+// scale by an Fp2 factor (extensions.rs:86-94)
+SY_HD_NOINLINE Fp6 fp6_scale(const Fp6& a, const Fp2& k) {
+  return Fp6{fp2_mul(a.c0, k), fp2_mul(a.c1, k), fp2_mul(a.c2, k)};
+}
+
+// Alg. 17 of eprint 2010/354 (fp6.rs:400-424)
+SY_HD_NOINLINE Fp6 fp6_inv(const Fp6& a) {
+  Fp2 t0 = fp2_sub(fp2_sqr(a.c0), fp2_mul(a.c1, fp2_mul_xi(a.c2)));
+  Fp2 t1 = fp2_sub(fp2_mul_xi(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
+  Fp2 t2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
+  Fp2 d = fp2_add(fp2_mul_xi(fp2_add(fp2_mul(a.c2, t1), fp2_mul(a.c1, t2))), fp2_mul(a.c0, t0));
+  d = fp2_inv(d);
+  return Fp6{fp2_mul(d, t0), fp2_mul(d, t1), fp2_mul(d, t2)};
+}
+
+// ------------------------------------------------------------------------------------------ Fp12
+SY_HD Fp12 fp12_one() { return Fp12{fp6_one(), fp6_zero()}; }
+SY_HD bool fp12_eq(const Fp12& a, const Fp12& b) { return fp6_eq(a.c0, b.c0) & fp6_eq(a.c1, b.c1); }
+// unitary_inverse (fp12.rs:381-383)
+SY_HD Fp12 fp12_conj(const Fp12& a) { return Fp12{a.c0, fp6_neg(a.c1)}; }
+
+// Karatsuba (fp12.rs:210-239)
+SY_HD_NOINLINE Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
+  Fp6 t0 = fp6_mul(a.c0, b.c0);
+  Fp6 t1 = fp6_mul(a.c1, b.c1);
+  Fp6 s = fp6_mul(fp6_add(a.c0, a.c1), fp6_add(b.c0, b.c1));
+  Fp12 r;
+  r.c0 = fp6_add(fp6_mul_v(t1), t0);
+  r.c1 = fp6_sub(fp6_sub(s, t0), t1);
+  return r;
+}
+
+// complex squaring (fp12.rs:536-550)
+SY_HD_NOINLINE Fp12 fp12_sqr(const Fp12& a) {
+  Fp6 c0 = fp6_sub(a.c0, a.c1);
+  Fp6 c3 = fp6_sub(a.c0, fp6_mul_v(a.c1));
+  Fp6 c2 = fp6_mul(a.c0, a.c1);
+  c0 = fp6_add(fp6_mul(c0, c3), c2);
+  Fp12 r;
+  r.c1 = fp6_dbl(c2);
+  r.c0 = fp6_add(c0, fp6_mul_v(c2));
+  return r;
+}
+
+// Alg. 23 of eprint 2010/354 (fp12.rs:270-287)
+SY_HD_NOINLINE Fp12 fp12_inv(const Fp12& a) {
+  Fp6 t = fp6_inv(fp6_sub(fp6_sqr(a.c0), fp6_mul_v(fp6_sqr(a.c1))));
+  return Fp12{fp6_mul(a.c0, t), fp6_neg(fp6_mul(a.c1, t))};
+}
+
+// Multiplication by the sparse element l0 + l_vv v^2 + l_vw v w, i.e. slots z0, z2, z4 of
+// (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2).  Same 13-product schedule as fp12.rs:426-503.
+SY_HD_NOINLINE Fp12 fp12_sparse_mul(const Fp12& f, const Fp2& x0, const Fp2& x4 /*ell_vw*/, const Fp2& x2 /*ell_vv*/) {
+  const Fp2 &z0 = f.c0.c0, &z1 = f.c0.c1, &z2 = f.c0.c2, &z3 = f.c1.c0, &z4 = f.c1.c1, &z5 = f.c1.c2;
+  Fp12 r;
+  Fp2 d0 = fp2_mul(z0, x0);
+  Fp2 d2 = fp2_mul(z2, x2);
+  Fp2 d4 = fp2_mul(z4, x4);
+  Fp2 s1 = fp2_mul(z1, x2);
+  r.c0.c0 = fp2_add(fp2_mul_xi(fp2_add(s1, d4)), d0);
+  Fp2 t3 = fp2_mul(z5, x4);
+  s1 = fp2_add(s1, t3);
+  Fp2 t4 = fp2_mul_xi(fp2_add(t3, d2));
+  t3 = fp2_mul(z1, x0);
+  s1 = fp2_add(s1, t3);
+  r.c0.c1 = fp2_add(t4, t3);
+  t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z2), fp2_add(x0, x2)), d0), d2);
+  t4 = fp2_mul(z3, x4);
+  s1 = fp2_add(s1, t4);
+  r.c0.c2 = fp2_add(t3, t4);
+  t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z2, z4), fp2_add(x2, x4)), d2), d4);
+  t4 = fp2_mul_xi(t3);
+  t3 = fp2_mul(z3, x0);
+  s1 = fp2_add(s1, t3);
+  r.c1.c0 = fp2_add(t4, t3);
+  t3 = fp2_mul(z5, x2);
+  s1 = fp2_add(s1, t3);
+  t4 = fp2_mul_xi(t3);
+  t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z4), fp2_add(x0, x4)), d0), d4);
+  r.c1.c1 = fp2_add(t4, t3);
+  Fp2 s0 = fp2_add(fp2_add(z1, z3), z5);
+  Fp2 t0 = fp2_add(fp2_add(x0, x2), x4);
+  r.c1.c2 = fp2_sub(fp2_mul(s0, t0), s1);
+  return r;
+}
+
+}  // namespace sylow

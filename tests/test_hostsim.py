@@ -1,0 +1,142 @@
+"""CPU tier: the DEVICE source (sylow_b200/csrc/*.cuh) compiled for the host (tests/hostsim) must agree
+with the oracle.  This checks tower/curve/pairing/hash logic before a B200 is available; the PTX
+primitives themselves are covered by the -m gpu tests."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bn254_py as o
+from tests import wire as w
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "hostsim", "libsylow_hostsim.so")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    src = os.path.join(HERE, "hostsim", "hostsim.cu")
+    csrc = os.path.join(os.path.dirname(HERE), "sylow_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["nvcc", "-x", "cu", "-O2", "-std=c++17", "-DSYLOW_HOSTSIM", "-shared", "-Xcompiler",
+                               "-fPIC", "-w", "-o", SO, src])
+    lib = ctypes.CDLL(SO)
+    lib.hs_hash_to_g1.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    lib.hs_hash_to_field.argtypes = lib.hs_hash_to_g1.argtypes
+    lib.hs_keccak256.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    return lib
+
+
+def _fp_op(hs, op, a, b=0):
+    out = ctypes.create_string_buffer(32)
+    hs.hs_fp_op(op, w.fp_b(a), w.fp_b(b), out)
+    return w.b_fp(out.raw)
+
+
+def test_fp_ops(hs):
+    rng = random.Random(1)
+    edge = [0, 1, 2, o.P - 1, o.P - 2, (o.P + 1) // 2, (1 << 253), (1 << 254) - 1 - (1 << 200)]
+    vals = edge + [rng.randrange(o.P) for _ in range(40)]
+    for a in vals:
+        for b in (vals[0], vals[3], rng.choice(vals), rng.randrange(o.P)):
+            assert _fp_op(hs, 0, a, b) == a * b % o.P
+            assert _fp_op(hs, 1, a, b) == (a + b) % o.P
+            assert _fp_op(hs, 2, a, b) == (a - b) % o.P
+        assert _fp_op(hs, 3, a) == o.fp_inv(a)
+        assert _fp_op(hs, 4, a) == a * o.TWO_INV % o.P
+        assert _fp_op(hs, 5, a) == 9 * a % o.P
+        assert _fp_op(hs, 6, a) == -a % o.P
+
+
+def _fp12_op(hs, op, a, b=None):
+    out = ctypes.create_string_buffer(384)
+    hs.hs_fp12_op(op, w.fp12_b(a), w.fp12_b(b if b is not None else a), out)
+    return w.b_fp12(out.raw)
+
+
+def test_fp12_ops(hs):
+    rng = random.Random(2)
+    for _ in range(4):
+        a, b = w.rand_fp12(rng), w.rand_fp12(rng)
+        assert _fp12_op(hs, 0, a, b) == o.fp12_mul(a, b)
+        assert _fp12_op(hs, 1, a) == o.fp12_sqr(a)
+        assert _fp12_op(hs, 2, a) == o.fp12_inv(a)
+        for e in (1, 2, 3):
+            assert _fp12_op(hs, 2 + e, a) == o.fp12_frobenius(a, e)
+        assert _fp12_op(hs, 7, a, b) == o.fp12_sparse_mul(a, b[0][0], b[0][1], b[0][2])
+    # cyclotomic squaring is only a squaring on the cyclotomic subgroup
+    g = o.pairing_affine(o.G1_GEN, o.G2_GEN)
+    assert _fp12_op(hs, 6, g) == o.cyclotomic_squared(g) == o.fp12_sqr(g)
+
+
+def test_pairing_generators(hs, kats):
+    out = ctypes.create_string_buffer(384)
+    hs.hs_pairing(w.g1_b(o.G1_GEN), w.g2_b(o.G2_GEN), out)
+    assert [w.b_fp(out.raw[32 * i: 32 * i + 32]) for i in range(12)] == [int(x, 16) for x in kats["gt_generator"]["fp12"]]
+
+
+def test_miller_and_final_exp_random(hs):
+    rng = random.Random(3)
+    p, q = w.rand_g1(rng), w.rand_g2(rng)
+    out = ctypes.create_string_buffer(384)
+    hs.hs_miller_loop(w.g1_b(p), w.g2_b(q), out)
+    f = o.miller_loop(o.g2_precompute(q), p)
+    assert w.b_fp12(out.raw) == f  # MillerLoopResult itself is bit-identical
+    out2 = ctypes.create_string_buffer(384)
+    hs.hs_final_exp(out.raw, out2)
+    assert w.b_fp12(out2.raw) == o.final_exponentiation(f)
+
+
+def test_scalar_mul(hs, kats):
+    rng = random.Random(4)
+    out = ctypes.create_string_buffer(64)
+    inp = bytes.fromhex(kats["eip196_mul"]["input"])
+    x, y, k = (int.from_bytes(inp[32 * i: 32 * i + 32], "big") for i in range(3))
+    assert hs.hs_g1_mul(w.g1_b((x, y)), 0, w.fp_b(k), out) == 0
+    exp = bytes.fromhex(kats["eip196_mul"]["expected"])
+    assert w.b_g1(out.raw)[:2] == (int.from_bytes(exp[:32], "big"), int.from_bytes(exp[32:], "big"))
+    p = w.rand_g1(rng)
+    for k in (0, 1, 2, o.R_ORDER, o.R_ORDER - 1, o.P - 1, rng.randrange(o.P)):
+        inf = hs.hs_g1_mul(w.g1_b(p), 0, w.fp_b(k), out)
+        ref = o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k))
+        assert (w.b_g1(out.raw, inf)) == ref
+    q = w.rand_g2(rng)
+    out = ctypes.create_string_buffer(128)
+    for k in (0, 1, o.R_ORDER - 1, rng.randrange(o.P)):
+        inf = hs.hs_g2_mul(w.g2_b(q), 0, w.fp_b(k), out)
+        ref = o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), k))
+        assert w.b_g2(out.raw, inf) == ref
+    # infinity in -> infinity out
+    out = ctypes.create_string_buffer(64)
+    assert hs.hs_g1_mul(w.g1_b((0, 1)), 1, w.fp_b(5), out) == 1 and w.b_g1(out.raw)[:2] == (0, 1)
+
+
+def test_g1_add_eip196(hs, kats):
+    inp = bytes.fromhex(kats["eip196_add"]["input"])
+    c = [int.from_bytes(inp[32 * i: 32 * i + 32], "big") for i in range(4)]
+    out = ctypes.create_string_buffer(64)
+    assert hs.hs_g1_add(w.g1_b(c[0:2]), 0, w.g1_b(c[2:4]), 0, out) == 0
+    exp = bytes.fromhex(kats["eip196_add"]["expected"])
+    assert w.b_g1(out.raw)[:2] == (int.from_bytes(exp[:32], "big"), int.from_bytes(exp[32:], "big"))
+    # P + (-P) = infinity, P + infinity = P
+    p = (c[0], c[1], False)
+    assert hs.hs_g1_add(w.g1_b(p), 0, w.g1_b(o.g1_affine_neg(p)), 0, out) == 1
+    assert hs.hs_g1_add(w.g1_b(p), 0, w.g1_b((0, 1)), 1, out) == 0 and w.b_g1(out.raw) == p
+
+
+def test_keccak_and_hash_to_curve(hs):
+    out = ctypes.create_string_buffer(32)
+    for m in (b"", b"abc", bytes(135), bytes(136), bytes(range(256)) * 3):
+        hs.hs_keccak256(m, len(m), out)
+        assert out.raw == o.keccak256(m)
+    dst_prime = o.DST + bytes([len(o.DST)])
+    rng = random.Random(5)
+    for m in (b"", (20).to_bytes(4, "big"), bytes(32), bytes(rng.randrange(256) for _ in range(200))):
+        o64 = ctypes.create_string_buffer(64)
+        hs.hs_hash_to_field(m, len(m), dst_prime, len(dst_prime), o64)
+        assert [w.b_fp(o64.raw[:32]), w.b_fp(o64.raw[32:])] == o.hash_to_field(m)
+        assert hs.hs_hash_to_g1(m, len(m), dst_prime, len(dst_prime), o64) == 0
+        assert w.b_g1(o64.raw) == o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m))
