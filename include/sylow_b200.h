@@ -1,0 +1,181 @@
+/* sylow_b200.h - C ABI of libsylow_b200.so, the B200-native batched BN254 engine.
+ *
+ * This is the drop-in boundary for sylow's data-parallel hot path.  sylow itself has no FFI
+ * (#![deny(unsafe_code)], /root/reference/src/lib.rs:63); these entry points are what a
+ * `sylow-cuda-sys` crate binds so that a sylow fork can add `pairing_batch`,
+ * `verify_batch`, `g1_mul_batch`, ... next to the functions they batch.  Each entry cites the
+ * reference interface it replaces.
+ *
+ * Wire formats (all host or device buffers are caller-owned, contiguous, AoS):
+ *   Fp        32 B   little-endian canonical integer in [0, p)  == Fp::value().to_words()  (fp.rs:232-234)
+ *   G1 affine 64 B   x || y                                     (groups/group.rs:174-181)
+ *   G2 affine 128 B  x.c0 || x.c1 || y.c0 || y.c1
+ *   Fp12 / Gt 384 B  12 Fp in tower order c0.c0.c0, c0.c0.c1, ..., c1.c2.c1   (fp12.rs:561-574)
+ *   scalar    32 B   little-endian integer < 2^256 (sylow passes an Fp-range value, group.rs:639-649)
+ *   infinity  parallel uint8 flag array (mirrors `infinity: Choice`); NULL = no point is infinite.
+ *
+ * Conventions: return 0 on success, a negative sylow_b200_status otherwise; never aborts; no
+ * callee-allocated memory is returned; a context is used by one call at a time and is bound to ONE
+ * CUDA device (one process or thread per GPU; shard batches as contiguous slices and combine the
+ * 384-byte Miller partial products with sylow_b200_fp12_product).  Host-pointer entry
+ * points are synchronous (results are in host memory on return).  The `_dev` entry points take
+ * DEVICE pointers (16-byte aligned) and enqueue on `stream` (a cudaStream_t passed as void*; NULL =
+ * the context's own stream) without synchronising - this is what bench.py times with inputs resident
+ * in HBM.  There is no CPU fallback: every entry point fails with SYLOW_B200_ERR_CUDA if no device
+ * is usable.
+ */
+#ifndef SYLOW_B200_H
+#define SYLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sylow_b200_ctx sylow_b200_ctx;
+
+typedef enum {
+  SYLOW_B200_OK = 0,
+  SYLOW_B200_ERR_ARG = -1,            /* NULL pointer, bad size, unsupported hash id, DST > 255 bytes */
+  SYLOW_B200_ERR_CUDA = -2,           /* CUDA runtime error (see sylow_b200_last_cuda_error) */
+  SYLOW_B200_ERR_NOT_ON_CURVE = -3,   /* GroupError::NotOnCurve      (groups/group.rs:37-47) */
+  SYLOW_B200_ERR_NOT_IN_SUBGROUP = -4,/* GroupError::NotInSubgroup */
+  SYLOW_B200_ERR_CANNOT_HASH = -5,    /* GroupError::CannotHashToGroup */
+  SYLOW_B200_ERR_DECODE = -6,         /* GroupError::DecodeError: a coordinate >= p */
+  SYLOW_B200_ERR_NOMEM = -7
+} sylow_b200_status;
+
+#define SYLOW_B200_HASH_KECCAK256 0   /* XMDExpander::<Keccak256>, lib.rs:181,225 */
+
+/* Context: owns one stream and growable device/pinned staging buffers on `device_id`. */
+int sylow_b200_create(sylow_b200_ctx** out, int device_id);
+int sylow_b200_destroy(sylow_b200_ctx* ctx);
+const char* sylow_b200_strerror(int status);
+/* cudaError_t of the last failing CUDA call on this context (0 if none). */
+int sylow_b200_last_cuda_error(const sylow_b200_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t sylow_b200_launch_count(const sylow_b200_ctx* ctx);
+
+/* ---- pairing --------------------------------------------------------------------------------- */
+
+/* n independent pairings, gt_out[i] = e(g1[i], g2[i]); an infinite input gives Gt::identity().
+ * Replaces a loop over `pairing(&G1Projective, &G2Projective) -> Gt`  (pairing.rs:870-893). */
+int sylow_b200_pairing_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                             const uint8_t* g2_inf, size_t n, uint8_t* gt_out /* n*384 */);
+
+/* n independent Miller loops, f_out[i] = G2Affine::precompute(g2[i]).miller_loop(g1[i]), canonical
+ * Fp12 (pairing.rs:676-708 composed with :590-619, bit-identical MillerLoopResult).  Infinite pairs give 1. */
+int sylow_b200_miller_loop_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                 const uint8_t* g2_inf, size_t n, uint8_t* f_out /* n*384 */);
+
+/* prod_i miller_loop(g2[i], g1[i]) == glued_miller_loop(&[G2PreComputed], &[G1Affine])  (pairing.rs:970-1022;
+ * equal bit-for-bit because Fp12 multiplication is exact and commutative).  Infinite pairs
+ * are skipped (contribute 1) - the reference's behaviour there is unpinned.  n = 0 gives 1. */
+int sylow_b200_miller_product(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                              const uint8_t* g2_inf, size_t n, uint8_t f_out[384]);
+
+/* gt_out[i] = MillerLoopResult::final_exponentiation(f[i])  (pairing.rs:245-492). */
+int sylow_b200_final_exp_batch(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t* gt_out /* n*384 */);
+
+/* out = prod_i f[i] in Fp12 (n = 0 gives 1).  Combines per-GPU Miller partial products (the
+ * `MulAssign for MillerLoopResult` of pairing.rs:63-68). */
+int sylow_b200_fp12_product(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t out[384]);
+
+/* n_checks independent product checks of pairs_per_check pairs each:
+ * ok_out[c] = (glued_pairing(g1s_c, g2s_c) == Gt::identity())  (pairing.rs:1029-1037; the ecPairing
+ * shape of examples/reth_bn128.rs:211-214).  Pair j of check c is element c*pairs_per_check + j. */
+int sylow_b200_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                   const uint8_t* g2_inf, size_t pairs_per_check, size_t n_checks, uint8_t* ok_out);
+
+/* ---- scalar multiplication --------------------------------------------------------------------- */
+
+/* out[i] = affine(scalars[i] * pts[i]);  replaces `&G1Projective * &Fp` + GroupAffine::from
+ * (groups/group.rs:639-667, :475-495).  out_inf may be NULL. */
+int sylow_b200_g1_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf,
+                            const uint8_t* scalars /* n*32 */, size_t n, uint8_t* out /* n*64 */, uint8_t* out_inf);
+int sylow_b200_g2_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts /* n*128 */, const uint8_t* pts_inf,
+                            const uint8_t* scalars /* n*32 */, size_t n, uint8_t* out /* n*128 */, uint8_t* out_inf);
+
+/* ---- hash to curve / BLS ------------------------------------------------------------------------ */
+
+/* out[i] = affine(G1Projective::hash_to_curve(XMDExpander::<Keccak256>::new(dst, 128), msg_i))
+ * (groups/g1.rs:307-331, hasher.rs:84-128,201-250, svdw.rs:180-262).  msg_i = msgs[offsets[i]..offsets[i+1]). */
+int sylow_b200_hash_to_g1_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets /* n+1 */, size_t n,
+                                const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out /* n*64 */,
+                                uint8_t* out_inf /* may be NULL */);
+
+/* sigs[i] = affine(sign(sk[i], msg_i)) = sk[i] * H(msg_i)   (lib.rs:179-187). */
+int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks /* n*32 */, const uint8_t* msgs,
+                          const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, int hash_id,
+                          uint8_t* sigs_out /* n*64 */);
+
+/* ok_out[i] = verify(pk[i], msg_i, sig[i]) = (e(sig, G2gen) == e(H(msg), pk))  (lib.rs:223-236),
+ * one boolean per signature. */
+int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks /* n*128 */, const uint8_t* msgs,
+                           const uint64_t* offsets, const uint8_t* sigs /* n*64 */, size_t n, const uint8_t* dst,
+                           size_t dst_len, int hash_id, uint8_t* ok_out);
+
+/* f_out = prod_i miller(sig_i, G2gen) * miller(-H(msg_i), pk_i): this GPU's 384-byte share of the
+ * batch check of examples/verify_multiple_messages_same_signer.rs:40-60. */
+int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs,
+                                    const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
+                                    size_t dst_len, int hash_id, uint8_t f_out[384]);
+
+/* *ok = (final_exponentiation(prod_i partials[i]) == Gt::identity()).  n_partials = number of GPUs. */
+int sylow_b200_verify_batch_finish(sylow_b200_ctx* ctx, const uint8_t* partials /* n_partials*384 */,
+                                   size_t n_partials, int* ok);
+
+/* Single-GPU convenience: partial + finish. */
+int sylow_b200_verify_batch(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs, const uint64_t* offsets,
+                            const uint8_t* sigs, size_t n, const uint8_t* dst, size_t dst_len, int hash_id, int* ok);
+
+/* ---- device-resident variants (DEVICE pointers, asynchronous on `stream`) ----------------------- */
+
+int sylow_b200_pairing_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
+                                 const uint8_t* d_g2, const uint8_t* d_g2_inf, size_t n, uint8_t* d_gt_out,
+                                 void* stream);
+int sylow_b200_miller_loop_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
+                                     const uint8_t* d_g2, const uint8_t* d_g2_inf, size_t n, uint8_t* d_f_out,
+                                     void* stream);
+int sylow_b200_miller_product_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
+                                  const uint8_t* d_g2, const uint8_t* d_g2_inf, size_t n, uint8_t* d_f_out,
+                                  void* stream);
+int sylow_b200_final_exp_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_f, size_t n, uint8_t* d_gt_out,
+                                   void* stream);
+int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
+                                       const uint8_t* d_g2, const uint8_t* d_g2_inf, size_t pairs_per_check,
+                                       size_t n_checks, uint8_t* d_ok_out, void* stream);
+int sylow_b200_g1_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_pts_inf,
+                                const uint8_t* d_scalars, size_t n, uint8_t* d_out, uint8_t* d_out_inf, void* stream);
+int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_pts_inf,
+                                const uint8_t* d_scalars, size_t n, uint8_t* d_out, uint8_t* d_out_inf, void* stream);
+int sylow_b200_hash_to_g1_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                                    const uint8_t* dst, size_t dst_len /* host */, int hash_id, uint8_t* d_out,
+                                    uint8_t* d_out_inf, void* stream);
+int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
+                                        const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n,
+                                        const uint8_t* dst, size_t dst_len /* host */, int hash_id,
+                                        uint8_t* d_f_out /* 384 */, void* stream);
+
+/* ---- diagnostics used by the parity tests and the roofline microbenchmark ---------------------- */
+
+/* out[i] = a[i] (op) b[i] on canonical Fp values; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 a/2, 5 -a. */
+int sylow_b200_fp_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* out[i] = a[i] (op) b[i] on Fp12; op: 0 mul, 1 sqr(a), 2 inv(a), 3/4/5 frobenius^{1,2,3}(a),
+ * 6 cyclotomic_squared(a), 7 a.sparse_mul(b.c0.c0, b.c0.c1, b.c0.c2). */
+int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* Register-resident throughput probes (the IMAD roofline denominator).  Every thread
+ * runs `iters` loop iterations.  variant 0/1/2: 1/2/4 interleaved dependent Montgomery multiplications
+ * per iteration (*ops_out = Fp multiplications; x136 = limb products).  variant 10: independent
+ * mad.wide.u32; 11: independent 32-bit mad.lo.u32; 12: mad.lo.cc/madc.hi.cc carry chains (the
+ * IMAD.WIDE.U32.X form fp_mul uses) - *ops_out = multiply-add instructions issued per thread x threads.
+ * *ms_out = device time of the second of two launches. */
+int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms_out,
+                          double* ops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYLOW_B200_H */

@@ -1,0 +1,290 @@
+"""Batched BN254 engine: Python host binding over the C ABI (include/sylow_b200.h).
+
+Arrays are numpy uint8 in the C-ABI wire formats (see the header): G1 (n, 64), G2 (n, 128),
+Fp12/Gt (n, 384), scalars (n, 32), infinity flags (n,) uint8.  The `_dev` methods take torch CUDA
+uint8 tensors and enqueue on torch's current stream (used by bench.py for the HBM-resident number).
+All compute happens in libsylow_b200.so on the GPU; nothing here computes field arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+DST = b"WARLOCK-CHAOS-V01-CS01-SHA-256"  # reference src/lib.rs:90
+
+
+def _u8(a, shape_tail: Optional[int], name: str) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if shape_tail is not None:
+        if a.ndim == 1 and a.size == shape_tail:
+            a = a.reshape(1, shape_tail)
+        if a.ndim != 2 or a.shape[1] != shape_tail:
+            raise ValueError("%s must have shape (n, %d), got %s" % (name, shape_tail, a.shape))
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pack_messages(msgs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """Concatenate messages into (buffer uint8, offsets uint64 of length n+1)."""
+    offs = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    if len(msgs):
+        offs[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if int(offs[-1]) else np.zeros(0, dtype=np.uint8)
+    return buf, offs
+
+
+class Engine:
+    """One context bound to one CUDA device (one process per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        st = self._lib.sylow_b200_create(ctypes.byref(h), int(device))
+        if st != 0:
+            raise _lib.SylowB200Error(st, "sylow_b200_create(device=%d)" % device)
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sylow_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st: int, where: str):
+        if st != 0:
+            raise _lib.SylowB200Error(st, where, self._lib.sylow_b200_last_cuda_error(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sylow_b200_launch_count(self._h))
+
+    # ------------------------------------------------------------------ pairing
+    def _pairs(self, g1, g2, g1_inf, g2_inf):
+        g1 = _u8(g1, 64, "g1")
+        g2 = _u8(g2, 128, "g2")
+        n = g1.shape[0]
+        if g2.shape[0] != n:
+            raise ValueError("g1 and g2 batch sizes differ: %d vs %d" % (n, g2.shape[0]))
+        g1_inf = None if g1_inf is None else np.ascontiguousarray(g1_inf, dtype=np.uint8).reshape(n)
+        g2_inf = None if g2_inf is None else np.ascontiguousarray(g2_inf, dtype=np.uint8).reshape(n)
+        return g1, g2, g1_inf, g2_inf, n
+
+    def pairing_batch(self, g1, g2, g1_inf=None, g2_inf=None) -> np.ndarray:
+        g1, g2, g1_inf, g2_inf, n = self._pairs(g1, g2, g1_inf, g2_inf)
+        out = np.empty((n, 384), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_pairing_batch(self._h, _ptr(g1), _ptr(g1_inf), _ptr(g2), _ptr(g2_inf), n,
+                                                    _ptr(out)), "pairing_batch")
+        return out
+
+    def miller_loop_batch(self, g1, g2, g1_inf=None, g2_inf=None) -> np.ndarray:
+        g1, g2, g1_inf, g2_inf, n = self._pairs(g1, g2, g1_inf, g2_inf)
+        out = np.empty((n, 384), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_miller_loop_batch(self._h, _ptr(g1), _ptr(g1_inf), _ptr(g2), _ptr(g2_inf), n,
+                                                        _ptr(out)), "miller_loop_batch")
+        return out
+
+    def miller_product(self, g1, g2, g1_inf=None, g2_inf=None) -> np.ndarray:
+        g1, g2, g1_inf, g2_inf, n = self._pairs(g1, g2, g1_inf, g2_inf)
+        out = np.empty(384, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_miller_product(self._h, _ptr(g1), _ptr(g1_inf), _ptr(g2), _ptr(g2_inf), n,
+                                                     _ptr(out)), "miller_product")
+        return out
+
+    def final_exp_batch(self, f) -> np.ndarray:
+        f = _u8(f, 384, "f")
+        out = np.empty_like(f)
+        self._ck(self._lib.sylow_b200_final_exp_batch(self._h, _ptr(f), f.shape[0], _ptr(out)), "final_exp_batch")
+        return out
+
+    def fp12_product(self, f) -> np.ndarray:
+        f = _u8(f, 384, "f")
+        out = np.empty(384, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_fp12_product(self._h, _ptr(f), f.shape[0], _ptr(out)), "fp12_product")
+        return out
+
+    def pairing_check_batch(self, g1, g2, pairs_per_check: int, g1_inf=None, g2_inf=None) -> np.ndarray:
+        g1, g2, g1_inf, g2_inf, n = self._pairs(g1, g2, g1_inf, g2_inf)
+        k = int(pairs_per_check)
+        if k <= 0 or n % k:
+            raise ValueError("batch of %d pairs is not a multiple of pairs_per_check=%d" % (n, k))
+        ok = np.empty(n // k, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_pairing_check_batch(self._h, _ptr(g1), _ptr(g1_inf), _ptr(g2), _ptr(g2_inf), k,
+                                                          n // k, _ptr(ok)), "pairing_check_batch")
+        return ok.astype(bool)
+
+    # ------------------------------------------------------------------ scalar multiplication
+    def _mul(self, fn, width, pts, scalars, pts_inf):
+        pts = _u8(pts, width, "pts")
+        scalars = _u8(scalars, 32, "scalars")
+        n = pts.shape[0]
+        if scalars.shape[0] != n:
+            raise ValueError("pts and scalars batch sizes differ")
+        pts_inf = None if pts_inf is None else np.ascontiguousarray(pts_inf, dtype=np.uint8).reshape(n)
+        out = np.empty((n, width), dtype=np.uint8)
+        out_inf = np.empty(n, dtype=np.uint8)
+        self._ck(fn(self._h, _ptr(pts), _ptr(pts_inf), _ptr(scalars), n, _ptr(out), _ptr(out_inf)), fn.__name__)
+        return out, out_inf
+
+    def g1_mul_batch(self, pts, scalars, pts_inf=None):
+        return self._mul(self._lib.sylow_b200_g1_mul_batch, 64, pts, scalars, pts_inf)
+
+    def g2_mul_batch(self, pts, scalars, pts_inf=None):
+        return self._mul(self._lib.sylow_b200_g2_mul_batch, 128, pts, scalars, pts_inf)
+
+    # ------------------------------------------------------------------ hash / BLS
+    @staticmethod
+    def _msgs(msgs):
+        if isinstance(msgs, tuple):
+            buf, offs = msgs
+            return np.ascontiguousarray(buf, dtype=np.uint8), np.ascontiguousarray(offs, dtype=np.uint64)
+        return pack_messages(msgs)
+
+    def hash_to_g1_batch(self, msgs, dst: bytes = DST):
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        out = np.empty((n, 64), dtype=np.uint8)
+        out_inf = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_hash_to_g1_batch(self._h, _ptr(buf), _ptr(offs), n, dst, len(dst),
+                                                       _lib.HASH_KECCAK256, _ptr(out), _ptr(out_inf)),
+                 "hash_to_g1_batch")
+        return out, out_inf
+
+    def sign_batch(self, sks, msgs, dst: bytes = DST) -> np.ndarray:
+        sks = _u8(sks, 32, "sks")
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        out = np.empty((n, 64), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_sign_batch(self._h, _ptr(sks), _ptr(buf), _ptr(offs), n, dst, len(dst),
+                                                 _lib.HASH_KECCAK256, _ptr(out)), "sign_batch")
+        return out
+
+    def verify_each(self, pks, msgs, sigs, dst: bytes = DST) -> np.ndarray:
+        pks = _u8(pks, 128, "pks")
+        sigs = _u8(sigs, 64, "sigs")
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        ok = np.empty(n, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_verify_each(self._h, _ptr(pks), _ptr(buf), _ptr(offs), _ptr(sigs), n, dst,
+                                                  len(dst), _lib.HASH_KECCAK256, _ptr(ok)), "verify_each")
+        return ok.astype(bool)
+
+    def verify_batch_partial(self, pks, msgs, sigs, dst: bytes = DST) -> np.ndarray:
+        pks = _u8(pks, 128, "pks")
+        sigs = _u8(sigs, 64, "sigs")
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        out = np.empty(384, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_verify_batch_partial(self._h, _ptr(pks), _ptr(buf), _ptr(offs), _ptr(sigs), n,
+                                                           dst, len(dst), _lib.HASH_KECCAK256, _ptr(out)),
+                 "verify_batch_partial")
+        return out
+
+    def verify_batch_finish(self, partials) -> bool:
+        partials = _u8(partials, 384, "partials")
+        ok = ctypes.c_int(0)
+        self._ck(self._lib.sylow_b200_verify_batch_finish(self._h, _ptr(partials), partials.shape[0],
+                                                          ctypes.byref(ok)), "verify_batch_finish")
+        return bool(ok.value)
+
+    def verify_batch(self, pks, msgs, sigs, dst: bytes = DST) -> bool:
+        return self.verify_batch_finish(self.verify_batch_partial(pks, msgs, sigs, dst).reshape(1, 384))
+
+    # ------------------------------------------------------------------ diagnostics
+    def fp_op_batch(self, op: int, a, b) -> np.ndarray:
+        a = _u8(a, 32, "a")
+        b = _u8(b, 32, "b")
+        out = np.empty_like(a)
+        self._ck(self._lib.sylow_b200_fp_op_batch(self._h, op, _ptr(a), _ptr(b), a.shape[0], _ptr(out)), "fp_op_batch")
+        return out
+
+    def fp12_op_batch(self, op: int, a, b) -> np.ndarray:
+        a = _u8(a, 384, "a")
+        b = _u8(b, 384, "b")
+        out = np.empty_like(a)
+        self._ck(self._lib.sylow_b200_fp12_op_batch(self._h, op, _ptr(a), _ptr(b), a.shape[0], _ptr(out)),
+                 "fp12_op_batch")
+        return out
+
+    def imad_probe(self, variant: int, blocks: int, threads: int, iters: int) -> Tuple[float, float]:
+        ms = ctypes.c_float(0)
+        ops = ctypes.c_double(0)
+        self._ck(self._lib.sylow_b200_imad_probe(self._h, variant, blocks, threads, iters, ctypes.byref(ms),
+                                                 ctypes.byref(ops)), "imad_probe")
+        return float(ms.value), float(ops.value)
+
+    # ------------------------------------------------------------------ device-resident (torch) variants
+    @staticmethod
+    def _tp(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def pairing_batch_dev(self, d_g1, d_g2, d_out, d_g1_inf=None, d_g2_inf=None):
+        n = d_g1.shape[0]
+        self._ck(self._lib.sylow_b200_pairing_batch_dev(self._h, self._tp(d_g1), self._tp(d_g1_inf), self._tp(d_g2),
+                                                        self._tp(d_g2_inf), n, self._tp(d_out), self._stream()),
+                 "pairing_batch_dev")
+
+    def miller_loop_batch_dev(self, d_g1, d_g2, d_out, d_g1_inf=None, d_g2_inf=None):
+        n = d_g1.shape[0]
+        self._ck(self._lib.sylow_b200_miller_loop_batch_dev(self._h, self._tp(d_g1), self._tp(d_g1_inf),
+                                                            self._tp(d_g2), self._tp(d_g2_inf), n, self._tp(d_out),
+                                                            self._stream()), "miller_loop_batch_dev")
+
+    def miller_product_dev(self, d_g1, d_g2, d_out, d_g1_inf=None, d_g2_inf=None):
+        n = d_g1.shape[0]
+        self._ck(self._lib.sylow_b200_miller_product_dev(self._h, self._tp(d_g1), self._tp(d_g1_inf), self._tp(d_g2),
+                                                         self._tp(d_g2_inf), n, self._tp(d_out), self._stream()),
+                 "miller_product_dev")
+
+    def final_exp_batch_dev(self, d_f, d_out):
+        self._ck(self._lib.sylow_b200_final_exp_batch_dev(self._h, self._tp(d_f), d_f.shape[0], self._tp(d_out),
+                                                          self._stream()), "final_exp_batch_dev")
+
+    def pairing_check_batch_dev(self, d_g1, d_g2, pairs_per_check, d_ok, d_g1_inf=None, d_g2_inf=None):
+        n = d_g1.shape[0]
+        self._ck(self._lib.sylow_b200_pairing_check_batch_dev(self._h, self._tp(d_g1), self._tp(d_g1_inf),
+                                                              self._tp(d_g2), self._tp(d_g2_inf), pairs_per_check,
+                                                              n // pairs_per_check, self._tp(d_ok), self._stream()),
+                 "pairing_check_batch_dev")
+
+    def g1_mul_batch_dev(self, d_pts, d_scalars, d_out, d_out_inf=None, d_pts_inf=None):
+        self._ck(self._lib.sylow_b200_g1_mul_batch_dev(self._h, self._tp(d_pts), self._tp(d_pts_inf),
+                                                       self._tp(d_scalars), d_pts.shape[0], self._tp(d_out),
+                                                       self._tp(d_out_inf), self._stream()), "g1_mul_batch_dev")
+
+    def g2_mul_batch_dev(self, d_pts, d_scalars, d_out, d_out_inf=None, d_pts_inf=None):
+        self._ck(self._lib.sylow_b200_g2_mul_batch_dev(self._h, self._tp(d_pts), self._tp(d_pts_inf),
+                                                       self._tp(d_scalars), d_pts.shape[0], self._tp(d_out),
+                                                       self._tp(d_out_inf), self._stream()), "g2_mul_batch_dev")
+
+    def hash_to_g1_batch_dev(self, d_msgs, d_offsets, d_out, d_out_inf=None, dst: bytes = DST):
+        n = d_offsets.shape[0] - 1
+        self._ck(self._lib.sylow_b200_hash_to_g1_batch_dev(self._h, self._tp(d_msgs), self._tp(d_offsets), n, dst,
+                                                           len(dst), _lib.HASH_KECCAK256, self._tp(d_out),
+                                                           self._tp(d_out_inf), self._stream()),
+                 "hash_to_g1_batch_dev")
+
+    def verify_batch_partial_dev(self, d_pks, d_msgs, d_offsets, d_sigs, d_f_out, dst: bytes = DST):
+        n = d_offsets.shape[0] - 1
+        self._ck(self._lib.sylow_b200_verify_batch_partial_dev(self._h, self._tp(d_pks), self._tp(d_msgs),
+                                                               self._tp(d_offsets), self._tp(d_sigs), n, dst,
+                                                               len(dst), _lib.HASH_KECCAK256, self._tp(d_f_out),
+                                                               self._stream()), "verify_batch_partial_dev")

@@ -1,0 +1,878 @@
+// libsylow_b200.so: kernels + C ABI (include/sylow_b200.h).  sm_100a only, no CPU fallback.
+#include "../../include/sylow_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hash.cuh"
+#include "wire.cuh"
+
+using namespace sylow;
+
+// ------------------------------------------------------------------------------------------------
+// kernels.  One item (pair / point / message / check) per thread; control flow is uniform across
+// a warp except for the infinity early-outs and the message-length loops of the hash.
+// ------------------------------------------------------------------------------------------------
+#define SY_MILLER_THREADS 128
+#define SY_FEXP_THREADS 128
+#define SY_MUL_THREADS 128
+#define SY_HASH_THREADS 128
+#define SY_SMALL_THREADS 128
+
+struct DstPrime {
+  uint8_t b[256];
+  uint32_t len;
+};
+
+// f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
+__global__ void __launch_bounds__(SY_MILLER_THREADS)
+k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, const uint8_t* __restrict__ g2,
+         const uint8_t* __restrict__ g2_inf, size_t g2_stride, size_t n, uint8_t* __restrict__ f_out, int raw_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t j = i * g2_stride;
+  bool inf = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[j]);
+  Fp12 f;
+  if (inf) {
+    f = fp12_one();
+  } else {
+    const uint8_t* p = g1 + i * 64;
+    const uint8_t* q = g2 + j * 128;
+    f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
+  }
+  if (raw_out)
+    fp12_store_raw(f_out + i * 384, f);
+  else
+    fp12_store(f_out + i * 384, f);
+}
+
+__global__ void __launch_bounds__(SY_FEXP_THREADS)
+k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 f = raw_in ? fp12_load_raw(f_in + i * 384) : fp12_load(f_in + i * 384);
+  fp12_store(gt_out + i * 384, final_exponentiation(f));
+}
+
+// out[t] = in[t] * in[t + T] * in[t + 2T] * ...   (Montgomery form in and out)
+__global__ void __launch_bounds__(SY_SMALL_THREADS)
+k_fp12_product_strided(const uint8_t* in, size_t n, uint8_t* out, size_t T) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fp12 acc = fp12_one();
+  bool first = true;
+  for (size_t i = t; i < n; i += T) {
+    Fp12 v = fp12_load_raw(in + i * 384);
+    acc = first ? v : fp12_mul(acc, v);
+    first = false;
+  }
+  fp12_store_raw(out + t * 384, acc);
+}
+
+// canonical <-> Montgomery for n Fp12 values
+__global__ void k_fp12_convert(const uint8_t* in, size_t n, uint8_t* out, int to_mont) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (to_mont)
+    fp12_store_raw(out + i * 384, fp12_load(in + i * 384));
+  else
+    fp12_store(out + i * 384, fp12_load_raw(in + i * 384));
+}
+
+// ok[c] = final_exp(prod_{j<k} f[c*k + j]) == 1
+__global__ void __launch_bounds__(SY_FEXP_THREADS)
+k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_checks) return;
+  Fp12 acc = fp12_one();
+  for (size_t j = 0; j < k; j++) {
+    Fp12 v = fp12_load_raw(f_raw + (c * k + j) * 384);
+    acc = j == 0 ? v : fp12_mul(acc, v);
+  }
+  ok[c] = fp12_eq(final_exponentiation(acc), fp12_one()) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(SY_MUL_THREADS)
+k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
+                     const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
+                     uint8_t* __restrict__ out_inf) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Aff a{fp_load(pts + i * 64), fp_load(pts + i * 64 + 32), pts_inf && pts_inf[i]};
+  Fp k = fp_load_raw(scalars + i * 32);
+  G1Aff r = proj_to_affine(proj_scalar_mul(affine_to_proj(a), k.l));
+  fp_store(out + i * 64, r.x);
+  fp_store(out + i * 64 + 32, r.y);
+  if (out_inf) out_inf[i] = r.inf;
+}
+
+__global__ void __launch_bounds__(SY_MUL_THREADS)
+k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
+                       const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
+                       uint8_t* __restrict__ out_inf) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G2Aff a{fp2_load(pts + i * 128), fp2_load(pts + i * 128 + 64), pts_inf && pts_inf[i]};
+  Fp k = fp_load_raw(scalars + i * 32);
+  G2Aff r = proj_to_affine(proj_scalar_mul(affine_to_proj(a), k.l));
+  fp2_store(out + i * 128, r.x);
+  fp2_store(out + i * 128 + 64, r.y);
+  if (out_inf) out_inf[i] = r.inf;
+}
+
+// out[i] = affine(+-hash_to_curve(msg_i)); status[i] = 1 if the SvdW sqrt check failed
+__global__ void __launch_bounds__(SY_HASH_THREADS)
+k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
+             const __grid_constant__ DstPrime dst, int negate, uint8_t* __restrict__ out,
+             uint8_t* __restrict__ out_inf, int* __restrict__ fail_flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o0 = offsets[i], o1 = offsets[i + 1];
+  G1Proj p;
+  bool ok = hash_to_g1(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, p);
+  if (!ok) atomicExch(fail_flag, 1);
+  G1Aff r = proj_to_affine(p);
+  if (negate && !r.inf) r.y = fp_neg(r.y);
+  fp_store(out + i * 64, r.x);
+  fp_store(out + i * 64 + 32, r.y);
+  if (out_inf) out_inf[i] = r.inf;
+}
+
+__global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x = fp_load(a + i * 32), y = fp_load(b + i * 32), r;
+  switch (op) {
+    case 0: r = fp_mul(x, y); break;
+    case 1: r = fp_add(x, y); break;
+    case 2: r = fp_sub(x, y); break;
+    case 3: r = fp_inv(x); break;
+    case 4: r = fp_halve(x); break;
+    default: r = fp_neg(x);
+  }
+  fp_store(out + i * 32, r);
+}
+
+__global__ void __launch_bounds__(SY_SMALL_THREADS)
+k_fp12_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 x = fp12_load(a + i * 384), y = fp12_load(b + i * 384), r;
+  switch (op) {
+    case 0: r = fp12_mul(x, y); break;
+    case 1: r = fp12_sqr(x); break;
+    case 2: r = fp12_inv(x); break;
+    case 3: r = fp12_frobenius(x, 1); break;
+    case 4: r = fp12_frobenius(x, 2); break;
+    case 5: r = fp12_frobenius(x, 3); break;
+    case 6: r = cyclotomic_squared(x); break;
+    default: r = fp12_sparse_mul(x, y.c0.c0, y.c0.c1, y.c0.c2);
+  }
+  fp12_store(out + i * 384, r);
+}
+
+// Register-resident Montgomery-multiplication throughput probe (the roofline denominator).
+template <int CHAINS>
+__global__ void k_imad_probe(int iters, const uint32_t* src, uint32_t* sink) {
+  Fp x[CHAINS], y;
+  for (int i = 0; i < 8; i++) y.l[i] = src[i];  // run-time multiplier: no constant folding
+  for (int c = 0; c < CHAINS; c++) {
+    x[c] = fp_one();
+    x[c].l[0] += threadIdx.x + c;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) x[c] = fp_mul(x[c], y);
+  }
+  uint32_t acc = 0;
+  for (int c = 0; c < CHAINS; c++)
+    for (int i = 0; i < 8; i++) acc ^= x[c].l[i];
+  if (acc == 0x12345678u) sink[0] = acc;  // practically never true; keeps the loop alive
+}
+
+// Raw pipe probes.  MODE 0: independent mad.wide.u32 (IMAD.WIDE.U32); MODE 1: independent 32-bit
+// mad.lo.u32 (IMAD); MODE 2: mad.lo.cc/madc.hi.cc carry chains of 4 pairs (IMAD.WIDE.U32.X with
+// predicate carries, the exact instruction form fp_mul uses).  64 multiply-adds per loop iteration.
+template <int MODE>
+__global__ void k_pipe_probe(int iters, const uint32_t* src, uint32_t* sink) {
+  uint32_t a = src[0] | 1u, b = src[1] | 3u;
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) r[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < (MODE == 1 ? 4 : 8); rep++) {
+      if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          uint64_t acc = ((uint64_t)r[2 * c + 1] << 32) | r[2 * c];
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(r[2 * c]));
+          r[2 * c] = (uint32_t)acc;
+          r[2 * c + 1] = (uint32_t)(acc >> 32);
+        }
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r[c]) : "r"(a), "r"(b));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          uint32_t* q = r + 8 * c;
+          asm volatile(
+              "mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+              "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+              "madc.lo.cc.u32 %2, %8, %9, %2;\n\t"
+              "madc.hi.cc.u32 %3, %8, %9, %3;\n\t"
+              "madc.lo.cc.u32 %4, %8, %9, %4;\n\t"
+              "madc.hi.cc.u32 %5, %8, %9, %5;\n\t"
+              "madc.lo.cc.u32 %6, %8, %9, %6;\n\t"
+              "madc.hi.u32 %7, %8, %9, %7;"
+              : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
+              : "r"(a), "r"(b));
+        }
+      }
+    }
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc ^= r[i];
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+};
+
+struct sylow_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int last_cuda = 0;
+  uint64_t launches = 0;
+  DevBuf in_a, in_b, in_c, in_d, flag_a, flag_b, out, scratch0, scratch1, scratch2;
+  int* d_fail = nullptr;
+};
+
+static int fail_cuda(sylow_b200_ctx* ctx, cudaError_t e) {
+  if (ctx) ctx->last_cuda = (int)e;
+  return SYLOW_B200_ERR_CUDA;
+}
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__); \
+  } while (0)
+#define CKS(call)                  \
+  do {                             \
+    int s__ = (call);              \
+    if (s__ != 0) return s__;      \
+  } while (0)
+
+static int reserve(sylow_b200_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t cap = bytes + (bytes >> 3) + 256;
+  cudaError_t e = cudaMalloc(&b.p, cap);
+  if (e != cudaSuccess) {
+    ctx->last_cuda = (int)e;
+    return e == cudaErrorMemoryAllocation ? SYLOW_B200_ERR_NOMEM : SYLOW_B200_ERR_CUDA;
+  }
+  b.cap = cap;
+  return 0;
+}
+
+static inline unsigned nblocks(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+static inline cudaStream_t pick(sylow_b200_ctx* ctx, void* stream) {
+  return stream ? (cudaStream_t)stream : ctx->stream;
+}
+#define LAUNCHED(ctx)        \
+  do {                       \
+    (ctx)->launches++;       \
+    CK(cudaGetLastError());  \
+  } while (0)
+
+extern "C" {
+
+int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
+  if (!out) return SYLOW_B200_ERR_ARG;
+  *out = nullptr;
+  sylow_b200_ctx* ctx = new (std::nothrow) sylow_b200_ctx();
+  if (!ctx) return SYLOW_B200_ERR_NOMEM;
+  ctx->device = device_id;
+  cudaError_t e = cudaSetDevice(device_id);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fail, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_fail, 0, sizeof(int));
+  if (e != cudaSuccess) {
+    delete ctx;
+    return SYLOW_B200_ERR_CUDA;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int sylow_b200_destroy(sylow_b200_ctx* ctx) {
+  if (!ctx) return SYLOW_B200_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  DevBuf* bufs[] = {&ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d, &ctx->flag_a,
+                    &ctx->flag_b, &ctx->out, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->d_fail) cudaFree(ctx->d_fail);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+const char* sylow_b200_strerror(int status) {
+  switch (status) {
+    case SYLOW_B200_OK: return "ok";
+    case SYLOW_B200_ERR_ARG: return "invalid argument";
+    case SYLOW_B200_ERR_CUDA: return "CUDA error";
+    case SYLOW_B200_ERR_NOT_ON_CURVE: return "point not on curve";
+    case SYLOW_B200_ERR_NOT_IN_SUBGROUP: return "point not in the r-torsion subgroup";
+    case SYLOW_B200_ERR_CANNOT_HASH: return "cannot hash to group";
+    case SYLOW_B200_ERR_DECODE: return "coordinate is not a canonical field element";
+    case SYLOW_B200_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+  }
+}
+int sylow_b200_last_cuda_error(const sylow_b200_ctx* ctx) { return ctx ? ctx->last_cuda : 0; }
+uint64_t sylow_b200_launch_count(const sylow_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------- device variants
+int sylow_b200_miller_loop_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                     const uint8_t* g2_inf, size_t n, uint8_t* f_out, void* stream) {
+  if (!ctx || (n && (!g1 || !g2 || !f_out))) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, pick(ctx, stream)>>>(g1, g1_inf, g2, g2_inf, 1, n,
+                                                                                    f_out, 0);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_final_exp_batch_dev(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t* gt_out, void* stream) {
+  if (!ctx || (n && (!f || !gt_out))) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  k_final_exp<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, pick(ctx, stream)>>>(f, 0, n, gt_out);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_pairing_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                 const uint8_t* g2_inf, size_t n, uint8_t* gt_out, void* stream) {
+  if (!ctx || (n && (!g1 || !g2 || !gt_out))) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  cudaStream_t s = pick(ctx, stream);
+  // Miller values (Montgomery form) are staged in gt_out itself; the final exponentiation is in place.
+  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, n, gt_out, 1);
+  LAUNCHED(ctx);
+  k_final_exp<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(gt_out, 1, n, gt_out);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+// reduce n Montgomery-form Fp12 values at `buf` (clobbered, with `tmp` as ping-pong space of at least
+// ceil(n/4) values) to one value written to d_out in canonical (raw_out = 0) or Montgomery form.
+static int product_reduce(sylow_b200_ctx* ctx, uint8_t* buf, uint8_t* tmp, size_t n, uint8_t* d_out, int raw_out,
+                          cudaStream_t s) {
+  uint8_t* cur = buf;
+  uint8_t* nxt = tmp;
+  while (n > 1) {
+    size_t T = n / 4;
+    if (T < 1) T = 1;
+    if (T > 148 * 256) T = 148 * 256;
+    k_fp12_product_strided<<<nblocks(T, SY_SMALL_THREADS), SY_SMALL_THREADS, 0, s>>>(cur, n, nxt, T);
+    LAUNCHED(ctx);
+    uint8_t* t = cur;
+    cur = nxt;
+    nxt = t;
+    n = T;
+  }
+  if (raw_out) {
+    CK(cudaMemcpyAsync(d_out, cur, 384, cudaMemcpyDeviceToDevice, s));
+  } else {
+    k_fp12_convert<<<1, 32, 0, s>>>(cur, 1, d_out, 0);
+    LAUNCHED(ctx);
+  }
+  return 0;
+}
+
+static const uint8_t kOneCanonical[384] = {1};
+
+int sylow_b200_miller_product_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                  const uint8_t* g2_inf, size_t n, uint8_t* f_out, void* stream) {
+  if (!ctx || !f_out || (n && (!g1 || !g2))) return SYLOW_B200_ERR_ARG;
+  cudaStream_t s = pick(ctx, stream);
+  if (!n) {
+    CK(cudaMemcpyAsync(f_out, kOneCanonical, 384, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  CKS(reserve(ctx, ctx->scratch0, n * 384));
+  CKS(reserve(ctx, ctx->scratch1, (n / 4 + 1) * 384));
+  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, n, ctx->scratch0.p, 1);
+  LAUNCHED(ctx);
+  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n, f_out, 0, s);
+}
+
+int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf,
+                                       const uint8_t* g2, const uint8_t* g2_inf, size_t k, size_t n_checks,
+                                       uint8_t* ok_out, void* stream) {
+  if (!ctx || (n_checks && !ok_out)) return SYLOW_B200_ERR_ARG;
+  if (!n_checks) return 0;
+  size_t n = k * n_checks;
+  if (n && (!g1 || !g2)) return SYLOW_B200_ERR_ARG;
+  cudaStream_t s = pick(ctx, stream);
+  if (n) {
+    CKS(reserve(ctx, ctx->scratch0, n * 384));
+    k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, n, ctx->scratch0.p, 1);
+    LAUNCHED(ctx);
+  }
+  k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, k, n_checks, ok_out);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_g1_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf,
+                                const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* out_inf, void* stream) {
+  if (!ctx || (n && (!pts || !scalars || !out))) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  k_g1_mul<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, pick(ctx, stream)>>>(pts, pts_inf, scalars, n,
+                                                                                        out, out_inf);
+  LAUNCHED(ctx);
+  return 0;
+}
+int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf,
+                                const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* out_inf, void* stream) {
+  if (!ctx || (n && (!pts || !scalars || !out))) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  k_g2_mul<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, pick(ctx, stream)>>>(pts, pts_inf, scalars,
+                                                                                          n, out, out_inf);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+static int make_dst_prime(const uint8_t* dst, size_t dst_len, int hash_id, DstPrime& dp) {
+  if (hash_id != SYLOW_B200_HASH_KECCAK256) return SYLOW_B200_ERR_ARG;
+  if (dst_len > 255 || (dst_len && !dst)) return SYLOW_B200_ERR_ARG;  // oversize DST (hasher.rs:158-163): not yet
+  memset(dp.b, 0, sizeof(dp.b));
+  if (dst_len) memcpy(dp.b, dst, dst_len);
+  dp.b[dst_len] = (uint8_t)dst_len;  // DST || I2OSP(len, 1)   (hasher.rs:205-209)
+  dp.len = (uint32_t)dst_len + 1;
+  return 0;
+}
+
+static int hash_launch(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                       const DstPrime& dp, int negate, uint8_t* d_out, uint8_t* d_out_inf, cudaStream_t s) {
+  k_hash_to_g1<<<nblocks(n, SY_HASH_THREADS), SY_HASH_THREADS, 0, s>>>(d_msgs, d_offsets, n, dp, negate, d_out,
+                                                                     d_out_inf, ctx->d_fail);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_hash_to_g1_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
+                                    const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* d_out,
+                                    uint8_t* d_out_inf, void* stream) {
+  if (!ctx || (n && (!d_offsets || !d_out))) return SYLOW_B200_ERR_ARG;
+  DstPrime dp;
+  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  if (!n) return 0;
+  return hash_launch(ctx, d_msgs, d_offsets, n, dp, 0, d_out, d_out_inf, pick(ctx, stream));
+}
+
+// G2 generator in wire form, uploaded once per context on first use
+static const uint64_t kG2GenWords[16] = {
+    // x.c0, x.c1, y.c0, y.c1 as 4 LE u64 words each (g2.rs:47-77)
+    5106727233969649389ull,  7440829307424791261ull,  4785637993704342649ull,  1729627375292849782ull,
+    10945020018377822914ull, 17413811393473931026ull, 8241798111626485029ull,  1841571559660931130ull,
+    5541340697920699818ull,  16416156555105522555ull, 5380518976772849807ull,  1353435754470862315ull,
+    6173549831154472795ull,  13567992399387660019ull, 17050234209342075797ull, 650358724130500725ull};
+
+// scratch layout for verify: [0, n*64) -H(m_i); then the G2 generator (128 B)
+static int verify_miller_values(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
+                                const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n, const DstPrime& dp,
+                                cudaStream_t s) {
+  // interleaved Miller values: f[2i] = miller(sig_i, G2gen), f[2i+1] = miller(-H(m_i), pk_i)
+  CKS(reserve(ctx, ctx->scratch0, 2 * n * 384));
+  CKS(reserve(ctx, ctx->scratch2, n * 64 + n + 128 + 64));
+  uint8_t* d_hm = ctx->scratch2.p;
+  uint8_t* d_hm_inf = d_hm + n * 64;
+  uint8_t* d_gen = d_hm + ((n * 65 + 63) / 64) * 64;
+  CK(cudaMemcpyAsync(d_gen, kG2GenWords, 128, cudaMemcpyHostToDevice, s));
+  CKS(hash_launch(ctx, d_msgs, d_offsets, n, dp, 1, d_hm, d_hm_inf, s));
+  // the two halves are written as two planes: [0,n) sig pairs, [n,2n) hash pairs
+  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(d_sigs, nullptr, d_gen, nullptr, 0, n,
+                                                                     ctx->scratch0.p, 1);
+  LAUNCHED(ctx);
+  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(d_hm, d_hm_inf, d_pks, nullptr, 1, n,
+                                                                     ctx->scratch0.p + n * 384, 1);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
+                                        const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n,
+                                        const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* d_f_out,
+                                        void* stream) {
+  if (!ctx || !d_f_out || (n && (!d_pks || !d_offsets || !d_sigs))) return SYLOW_B200_ERR_ARG;
+  DstPrime dp;
+  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  cudaStream_t s = pick(ctx, stream);
+  if (!n) {
+    CK(cudaMemcpyAsync(d_f_out, kOneCanonical, 384, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  CKS(verify_miller_values(ctx, d_pks, d_msgs, d_offsets, d_sigs, n, dp, s));
+  CKS(reserve(ctx, ctx->scratch1, (2 * n / 4 + 1) * 384));
+  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, 2 * n, d_f_out, 0, s);
+}
+
+// ------------------------------------------------------------------------------- host variants
+static int to_dev(sylow_b200_ctx* ctx, DevBuf& b, const void* h, size_t bytes, const uint8_t** d) {
+  *d = nullptr;
+  if (!h || !bytes) return 0;
+  CKS(reserve(ctx, b, bytes));
+  CK(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *d = b.p;
+  return 0;
+}
+static int finish(sylow_b200_ctx* ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+#define ENTER(ctx)                                \
+  if (!(ctx)) return SYLOW_B200_ERR_ARG;          \
+  CK(cudaSetDevice((ctx)->device));
+
+int sylow_b200_pairing_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                             const uint8_t* g2_inf, size_t n, uint8_t* gt_out) {
+  ENTER(ctx);
+  if (n && (!g1 || !g2 || !gt_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *d1, *d1i, *d2, *d2i;
+  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
+  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  CKS(sylow_b200_pairing_batch_dev(ctx, d1, d1i, d2, d2i, n, ctx->out.p, nullptr));
+  CK(cudaMemcpyAsync(gt_out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_miller_loop_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                 const uint8_t* g2_inf, size_t n, uint8_t* f_out) {
+  ENTER(ctx);
+  if (n && (!g1 || !g2 || !f_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *d1, *d1i, *d2, *d2i;
+  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
+  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  CKS(sylow_b200_miller_loop_batch_dev(ctx, d1, d1i, d2, d2i, n, ctx->out.p, nullptr));
+  CK(cudaMemcpyAsync(f_out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_miller_product(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                              const uint8_t* g2_inf, size_t n, uint8_t f_out[384]) {
+  ENTER(ctx);
+  if (!f_out || (n && (!g1 || !g2))) return SYLOW_B200_ERR_ARG;
+  const uint8_t *d1, *d1i, *d2, *d2i;
+  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
+  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
+  CKS(reserve(ctx, ctx->out, 384));
+  CKS(sylow_b200_miller_product_dev(ctx, d1, d1i, d2, d2i, n, ctx->out.p, nullptr));
+  CK(cudaMemcpyAsync(f_out, ctx->out.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_final_exp_batch(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t* gt_out) {
+  ENTER(ctx);
+  if (n && (!f || !gt_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t* df;
+  CKS(to_dev(ctx, ctx->in_a, f, n * 384, &df));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  CKS(sylow_b200_final_exp_batch_dev(ctx, df, n, ctx->out.p, nullptr));
+  CK(cudaMemcpyAsync(gt_out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_fp12_product(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t out[384]) {
+  ENTER(ctx);
+  if (!out || (n && !f)) return SYLOW_B200_ERR_ARG;
+  if (!n) {
+    memcpy(out, kOneCanonical, 384);
+    return 0;
+  }
+  const uint8_t* df;
+  CKS(to_dev(ctx, ctx->in_a, f, n * 384, &df));
+  CKS(reserve(ctx, ctx->scratch0, n * 384));
+  CKS(reserve(ctx, ctx->scratch1, (n / 4 + 1) * 384));
+  CKS(reserve(ctx, ctx->out, 384));
+  k_fp12_convert<<<nblocks(n, 128), 128, 0, ctx->stream>>>(df, n, ctx->scratch0.p, 1);
+  LAUNCHED(ctx);
+  CKS(product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n, ctx->out.p, 0, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->out.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                                   const uint8_t* g2_inf, size_t k, size_t n_checks, uint8_t* ok_out) {
+  ENTER(ctx);
+  if (n_checks && !ok_out) return SYLOW_B200_ERR_ARG;
+  if (!n_checks) return 0;
+  size_t n = k * n_checks;
+  if (n && (!g1 || !g2)) return SYLOW_B200_ERR_ARG;
+  const uint8_t *d1, *d1i, *d2, *d2i;
+  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
+  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
+  CKS(reserve(ctx, ctx->out, n_checks));
+  CKS(sylow_b200_pairing_check_batch_dev(ctx, d1, d1i, d2, d2i, k, n_checks, ctx->out.p, nullptr));
+  CK(cudaMemcpyAsync(ok_out, ctx->out.p, n_checks, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+static int mul_host(sylow_b200_ctx* ctx, int g2, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars,
+                    size_t n, uint8_t* out, uint8_t* out_inf) {
+  ENTER(ctx);
+  if (n && (!pts || !scalars || !out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  size_t pb = g2 ? 128 : 64;
+  const uint8_t *dp, *dpi, *dk;
+  CKS(to_dev(ctx, ctx->in_a, pts, n * pb, &dp));
+  CKS(to_dev(ctx, ctx->flag_a, pts_inf, n, &dpi));
+  CKS(to_dev(ctx, ctx->in_b, scalars, n * 32, &dk));
+  CKS(reserve(ctx, ctx->out, n * pb));
+  CKS(reserve(ctx, ctx->flag_b, n));
+  if (g2)
+    CKS(sylow_b200_g2_mul_batch_dev(ctx, dp, dpi, dk, n, ctx->out.p, ctx->flag_b.p, nullptr));
+  else
+    CKS(sylow_b200_g1_mul_batch_dev(ctx, dp, dpi, dk, n, ctx->out.p, ctx->flag_b.p, nullptr));
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * pb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_inf) CK(cudaMemcpyAsync(out_inf, ctx->flag_b.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+int sylow_b200_g1_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars,
+                            size_t n, uint8_t* out, uint8_t* out_inf) {
+  return mul_host(ctx, 0, pts, pts_inf, scalars, n, out, out_inf);
+}
+int sylow_b200_g2_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars,
+                            size_t n, uint8_t* out, uint8_t* out_inf) {
+  return mul_host(ctx, 1, pts, pts_inf, scalars, n, out, out_inf);
+}
+
+static int check_hash_fail(sylow_b200_ctx* ctx) {
+  int f = 0;
+  CK(cudaMemcpyAsync(&f, ctx->d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (f) {
+    CK(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), ctx->stream));
+    return SYLOW_B200_ERR_CANNOT_HASH;
+  }
+  return 0;
+}
+
+static int msgs_to_dev(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                       const uint8_t** d_msgs, const uint64_t** d_off) {
+  if (!offsets) return SYLOW_B200_ERR_ARG;
+  if (offsets[0] != 0) return SYLOW_B200_ERR_ARG;
+  for (size_t i = 0; i < n; i++)
+    if (offsets[i + 1] < offsets[i]) return SYLOW_B200_ERR_ARG;
+  size_t total = (size_t)offsets[n];
+  if (total && !msgs) return SYLOW_B200_ERR_ARG;
+  const uint8_t* dm;
+  const uint8_t* dof;
+  CKS(to_dev(ctx, ctx->in_c, msgs, total, &dm));
+  if (!dm) {  // all messages empty: still need a valid pointer
+    CKS(reserve(ctx, ctx->in_c, 16));
+    dm = ctx->in_c.p;
+  }
+  CKS(to_dev(ctx, ctx->in_d, offsets, (n + 1) * sizeof(uint64_t), &dof));
+  *d_msgs = dm;
+  *d_off = reinterpret_cast<const uint64_t*>(dof);
+  return 0;
+}
+
+int sylow_b200_hash_to_g1_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out, uint8_t* out_inf) {
+  ENTER(ctx);
+  DstPrime dp;
+  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  if (!n) return 0;
+  if (!out) return SYLOW_B200_ERR_ARG;
+  const uint8_t* dm;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(reserve(ctx, ctx->out, n * 64));
+  CKS(reserve(ctx, ctx->flag_b, n));
+  CKS(hash_launch(ctx, dm, dof, n, dp, 0, ctx->out.p, ctx->flag_b.p, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_inf) CK(cudaMemcpyAsync(out_inf, ctx->flag_b.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_hash_fail(ctx);
+}
+
+int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks, const uint8_t* msgs, const uint64_t* offsets,
+                          size_t n, const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* sigs_out) {
+  ENTER(ctx);
+  DstPrime dp;
+  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  if (!n) return 0;
+  if (!sks || !sigs_out) return SYLOW_B200_ERR_ARG;
+  const uint8_t *dm, *dk;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(to_dev(ctx, ctx->in_b, sks, n * 32, &dk));
+  CKS(reserve(ctx, ctx->scratch2, n * 65));
+  CKS(reserve(ctx, ctx->out, n * 64));
+  CKS(hash_launch(ctx, dm, dof, n, dp, 0, ctx->scratch2.p, ctx->scratch2.p + n * 64, ctx->stream));
+  CKS(sylow_b200_g1_mul_batch_dev(ctx, ctx->scratch2.p, ctx->scratch2.p + n * 64, dk, n, ctx->out.p, nullptr, nullptr));
+  CK(cudaMemcpyAsync(sigs_out, ctx->out.p, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_hash_fail(ctx);
+}
+
+int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs,
+                                    const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
+                                    size_t dst_len, int hash_id, uint8_t f_out[384]) {
+  ENTER(ctx);
+  if (!f_out) return SYLOW_B200_ERR_ARG;
+  DstPrime dp;
+  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  if (!n) {
+    memcpy(f_out, kOneCanonical, 384);
+    return 0;
+  }
+  if (!pks || !sigs) return SYLOW_B200_ERR_ARG;
+  const uint8_t *dm, *dpk, *dsg;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(to_dev(ctx, ctx->in_a, pks, n * 128, &dpk));
+  CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
+  CKS(reserve(ctx, ctx->out, 384));
+  CKS(sylow_b200_verify_batch_partial_dev(ctx, dpk, dm, dof, dsg, n, dst, dst_len, hash_id, ctx->out.p, nullptr));
+  CK(cudaMemcpyAsync(f_out, ctx->out.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_hash_fail(ctx);
+}
+
+int sylow_b200_verify_batch_finish(sylow_b200_ctx* ctx, const uint8_t* partials, size_t n_partials, int* ok) {
+  ENTER(ctx);
+  if (!ok || (n_partials && !partials)) return SYLOW_B200_ERR_ARG;
+  uint8_t prod[384], gt[384];
+  CKS(sylow_b200_fp12_product(ctx, partials, n_partials, prod));
+  CKS(sylow_b200_final_exp_batch(ctx, prod, 1, gt));
+  *ok = memcmp(gt, kOneCanonical, 384) == 0;
+  return 0;
+}
+
+int sylow_b200_verify_batch(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs, const uint64_t* offsets,
+                            const uint8_t* sigs, size_t n, const uint8_t* dst, size_t dst_len, int hash_id, int* ok) {
+  if (!ok) return SYLOW_B200_ERR_ARG;
+  uint8_t f[384];
+  CKS(sylow_b200_verify_batch_partial(ctx, pks, msgs, offsets, sigs, n, dst, dst_len, hash_id, f));
+  return sylow_b200_verify_batch_finish(ctx, f, 1, ok);
+}
+
+int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs, const uint64_t* offsets,
+                           const uint8_t* sigs, size_t n, const uint8_t* dst, size_t dst_len, int hash_id,
+                           uint8_t* ok_out) {
+  ENTER(ctx);
+  DstPrime dp;
+  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  if (!n) return 0;
+  if (!pks || !sigs || !ok_out) return SYLOW_B200_ERR_ARG;
+  const uint8_t *dm, *dpk, *dsg;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(to_dev(ctx, ctx->in_a, pks, n * 128, &dpk));
+  CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
+  CKS(verify_miller_values(ctx, dpk, dm, dof, dsg, n, dp, ctx->stream));
+  // planes [0,n) and [n,2n): multiply plane-wise (T = n), then one final exp + compare per signature
+  CKS(reserve(ctx, ctx->scratch1, n * 384));
+  CKS(reserve(ctx, ctx->out, n));
+  k_fp12_product_strided<<<nblocks(n, SY_SMALL_THREADS), SY_SMALL_THREADS, 0, ctx->stream>>>(ctx->scratch0.p, 2 * n,
+                                                                                           ctx->scratch1.p, n);
+  LAUNCHED(ctx);
+  k_check_products<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(ctx->scratch1.p, 1, n, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(ok_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_hash_fail(ctx);
+}
+
+// ------------------------------------------------------------------------------- diagnostics
+int sylow_b200_fp_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  ENTER(ctx);
+  if (n && (!a || !b || !out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *da, *db;
+  CKS(to_dev(ctx, ctx->in_a, a, n * 32, &da));
+  CKS(to_dev(ctx, ctx->in_b, b, n * 32, &db));
+  CKS(reserve(ctx, ctx->out, n * 32));
+  k_fp_op<<<nblocks(n, 128), 128, 0, ctx->stream>>>(op, da, db, n, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  ENTER(ctx);
+  if (n && (!a || !b || !out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *da, *db;
+  CKS(to_dev(ctx, ctx->in_a, a, n * 384, &da));
+  CKS(to_dev(ctx, ctx->in_b, b, n * 384, &db));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  k_fp12_op<<<nblocks(n, SY_SMALL_THREADS), SY_SMALL_THREADS, 0, ctx->stream>>>(op, da, db, n, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms_out,
+                          double* ops_out) {
+  ENTER(ctx);
+  if (!ms_out || !ops_out || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return SYLOW_B200_ERR_ARG;
+  CKS(reserve(ctx, ctx->out, 256));
+  CK(cudaMemsetAsync(ctx->out.p, 0x5a, 256, ctx->stream));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(ctx->out.p);
+  uint32_t* sink = reinterpret_cast<uint32_t*>(ctx->out.p) + 32;
+  double per_thread_iter = 0;
+  for (int rep = 0; rep < 2; rep++) {  // the first pass warms up
+    CK(cudaEventRecord(e0, ctx->stream));
+    switch (variant) {
+      case 0: k_imad_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
+      case 1: k_imad_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 2; break;
+      case 2: k_imad_probe<4><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 4; break;
+      case 10: k_pipe_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
+      case 11: k_pipe_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
+      case 12: k_pipe_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
+      default: return SYLOW_B200_ERR_ARG;
+    }
+    LAUNCHED(ctx);
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+  }
+  CK(cudaEventElapsedTime(ms_out, e0, e1));
+  *ops_out = (double)blocks * threads * (double)iters * per_thread_iter;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
+}  // extern "C"

