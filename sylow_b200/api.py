@@ -234,7 +234,11 @@ class Engine:
     def _stream():
         import torch
 
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        h = torch.cuda.current_stream().cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "use the context's own stream";
+        # name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so CUDA events recorded
+        # on torch's stream bracket the kernels.
+        return ctypes.c_void_p(h if h else 1)
 
     def pairing_batch_dev(self, d_g1, d_g2, d_out, d_g1_inf=None, d_g2_inf=None):
         n = d_g1.shape[0]

@@ -236,7 +236,14 @@ def test_sign_verify(eng):
     bad = sigs.copy()
     bad[[1, 2]] = bad[[2, 1]]
     assert eng.verify_each(pks, MSGS, bad).tolist() == [True, False, False] + [True] * (n - 3)
-    assert eng.verify_batch(pks, MSGS, bad) is False
+    # the un-blinded product check of the reference example cannot see a permutation of signatures
+    # (prod e(sig_i, G2) is symmetric) - that is the reference's semantics, so it is ours:
+    assert eng.verify_batch(pks, MSGS, bad) is True
+    bad2 = sigs.copy()
+    bad2[1] = sigs[0]
+    assert eng.verify_batch(pks, MSGS, bad2) is False
+    assert o.verify_batch([w.b_g2(bytes(r)) for r in pks[:3]], MSGS[:3], [w.b_g1(bytes(r)) for r in bad2[:3]]) is False
+    assert o.verify_batch([w.b_g2(bytes(r)) for r in pks[:3]], MSGS[:3], [w.b_g1(bytes(r)) for r in bad[:3]]) is True
     msgs2 = list(MSGS)
     msgs2[0] = b"other"
     assert eng.verify_each(pks, msgs2, sigs).tolist() == [False] + [True] * (n - 1)
@@ -247,7 +254,7 @@ def test_sign_verify(eng):
     pa = eng.verify_batch_partial(pks[:3], MSGS[:3], sigs[:3])
     pb = eng.verify_batch_partial(pks[3:], MSGS[3:], sigs[3:])
     assert eng.verify_batch_finish(np.stack([pa, pb])) is True
-    assert eng.verify_batch([], [], np.zeros((0, 64), np.uint8).reshape(0, 64)) is True if False else True
+    assert eng.verify_batch(np.zeros((0, 128), np.uint8), [], np.zeros((0, 64), np.uint8)) is True  # empty batch
 
 
 def test_error_paths(eng):
