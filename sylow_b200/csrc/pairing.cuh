@@ -8,6 +8,23 @@
 #pragma once
 #include "curve.cuh"
 
+// Optional block-wide re-convergence inside the long loops: keeps the warps of a block in the same
+// region of the (large) instruction stream so instruction-cache lines fetched by one warp are hit by
+// the others.  Only legal when every thread of the block runs the loop (the kernels guarantee it).
+#ifndef SY_BLOCK_SYNC
+#define SY_BLOCK_SYNC 1
+#endif
+#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
+#define SY_LOOP_SYNC() __syncthreads()
+#else
+#define SY_LOOP_SYNC() ((void)0)
+#endif
+#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 2
+#define SY_STEP_SYNC() __syncthreads()
+#else
+#define SY_STEP_SYNC() ((void)0)
+#endif
+
 namespace sylow {
 
 struct Ell {
@@ -62,12 +79,17 @@ SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const
   Fp2 nqy = fp2_neg(qy);
   Fp12 f = fp12_one();
   for (int i = 0; i < 64; i++) {
+    SY_LOOP_SYNC();
     Ell l = g2_doubling_step(r);
+    SY_STEP_SYNC();
     if (i != 0) f = fp12_sqr(f);  // 1^2 = 1
+    SY_STEP_SYNC();
     f = miller_mul_line(f, l, xp, yp);
     int digit = SY_TAB(kAteNaf)[i];
     if (digit != 0) {
+      SY_STEP_SYNC();
       l = g2_addition_step(r, qx, digit > 0 ? qy : nqy);
+      SY_STEP_SYNC();
       f = miller_mul_line(f, l, xp, yp);
     }
   }
@@ -134,8 +156,12 @@ SY_HD_NOINLINE Fp12 cyclotomic_squared(const Fp12& f) {
 SY_HD_NOINLINE Fp12 exp_by_neg_z(const Fp12& f) {
   Fp12 res = f;
   for (int i = 61; i >= 0; i--) {
+    SY_LOOP_SYNC();
     res = cyclotomic_squared(res);
-    if ((SY_BLS_X >> i) & 1) res = fp12_mul(res, f);
+    if ((SY_BLS_X >> i) & 1) {
+      SY_STEP_SYNC();
+      res = fp12_mul(res, f);
+    }
   }
   return fp12_conj(res);
 }
@@ -143,7 +169,9 @@ SY_HD_NOINLINE Fp12 exp_by_neg_z(const Fp12& f) {
 // pairing.rs:245-492
 SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
   // easy part (:410-415)
+  SY_LOOP_SYNC();
   Fp12 f = fp12_mul(fp12_conj(f0), fp12_inv(f0));
+  SY_LOOP_SYNC();
   Fp12 inp = fp12_mul(fp12_frobenius(f, 2), f);
   // hard part (:437-489)
   Fp12 a = exp_by_neg_z(inp);
@@ -152,10 +180,13 @@ SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
   Fp12 d = fp12_mul(c, b);
   Fp12 e = exp_by_neg_z(d);
   Fp12 g = exp_by_neg_z(cyclotomic_squared(e));
+  SY_LOOP_SYNC();
   Fp12 k = fp12_mul(fp12_mul(fp12_conj(g), e), fp12_conj(d));
   Fp12 l = fp12_mul(k, b);
+  SY_LOOP_SYNC();
   Fp12 n = fp12_mul(inp, fp12_mul(k, e));
   Fp12 p = fp12_mul(fp12_frobenius(l, 1), n);
+  SY_LOOP_SYNC();
   Fp12 r = fp12_mul(fp12_frobenius(k, 2), p);
   Fp12 u = fp12_frobenius(fp12_mul(fp12_conj(inp), l), 3);
   return fp12_mul(u, r);

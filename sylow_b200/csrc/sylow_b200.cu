@@ -16,8 +16,18 @@ using namespace sylow;
 // kernels.  One item (pair / point / message / check) per thread; control flow is uniform across
 // a warp except for the infinity early-outs and the message-length loops of the hash.
 // ------------------------------------------------------------------------------------------------
-#define SY_MILLER_THREADS 128
-#define SY_FEXP_THREADS 128
+#ifndef SY_MILLER_THREADS
+#define SY_MILLER_THREADS 256
+#endif
+#ifndef SY_MILLER_MINB
+#define SY_MILLER_MINB 1
+#endif
+#ifndef SY_FEXP_THREADS
+#define SY_FEXP_THREADS 256
+#endif
+#ifndef SY_FEXP_MINB
+#define SY_FEXP_MINB 1
+#endif
 #define SY_MUL_THREADS 128
 #define SY_HASH_THREADS 128
 #define SY_SMALL_THREADS 128
@@ -28,33 +38,34 @@ struct DstPrime {
 };
 
 // f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
-__global__ void __launch_bounds__(SY_MILLER_THREADS)
+__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
 k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, const uint8_t* __restrict__ g2,
          const uint8_t* __restrict__ g2_inf, size_t g2_stride, size_t n, uint8_t* __restrict__ f_out, int raw_out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // Every thread of the block runs the loop (SY_LOOP_SYNC needs that): out-of-range threads redo the
+  // last item and discard it; infinite pairs are computed on whatever bytes are there and replaced by 1.
+  size_t i = i0 < n ? i0 : n - 1;
   size_t j = i * g2_stride;
   bool inf = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[j]);
-  Fp12 f;
-  if (inf) {
-    f = fp12_one();
-  } else {
-    const uint8_t* p = g1 + i * 64;
-    const uint8_t* q = g2 + j * 128;
-    f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
-  }
+  const uint8_t* p = g1 + i * 64;
+  const uint8_t* q = g2 + j * 128;
+  Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
+  if (i0 >= n) return;
+  if (inf) f = fp12_one();
   if (raw_out)
     fp12_store_raw(f_out + i * 384, f);
   else
     fp12_store(f_out + i * 384, f);
 }
 
-__global__ void __launch_bounds__(SY_FEXP_THREADS)
+__global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
 k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;  // all threads run the loops (SY_LOOP_SYNC); the surplus is discarded
   Fp12 f = raw_in ? fp12_load_raw(f_in + i * 384) : fp12_load(f_in + i * 384);
-  fp12_store(gt_out + i * 384, final_exponentiation(f));
+  Fp12 g = final_exponentiation(f);
+  if (i0 >= n) return;
+  fp12_store(gt_out + i * 384, g);
 }
 
 // out[t] = in[t] * in[t + T] * in[t + 2T] * ...   (Montgomery form in and out)
@@ -83,16 +94,18 @@ __global__ void k_fp12_convert(const uint8_t* in, size_t n, uint8_t* out, int to
 }
 
 // ok[c] = final_exp(prod_{j<k} f[c*k + j]) == 1
-__global__ void __launch_bounds__(SY_FEXP_THREADS)
+__global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
 k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
-  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_checks) return;
+  size_t c0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t c = c0 < n_checks ? c0 : n_checks - 1;
   Fp12 acc = fp12_one();
   for (size_t j = 0; j < k; j++) {
     Fp12 v = fp12_load_raw(f_raw + (c * k + j) * 384);
     acc = j == 0 ? v : fp12_mul(acc, v);
   }
-  ok[c] = fp12_eq(final_exponentiation(acc), fp12_one()) ? 1 : 0;
+  bool one = fp12_eq(final_exponentiation(acc), fp12_one());
+  if (c0 >= n_checks) return;
+  ok[c] = one ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(SY_MUL_THREADS)

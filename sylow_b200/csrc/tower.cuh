@@ -6,6 +6,18 @@
 #pragma once
 #include "fp.cuh"
 
+// SY_SMALL_CODE=1 keeps the cheap Fp2 operations (add/sub/double/negate/halve/xi) out of line too, which
+// shrinks the hot instruction footprint of the pairing kernels several-fold (profiles/: the dominant
+// stall of the fully inlined build was instruction fetch).
+#ifndef SY_SMALL_CODE
+#define SY_SMALL_CODE 0
+#endif
+#if SY_SMALL_CODE
+#define SY_HD_ADD SY_HD_NOINLINE
+#else
+#define SY_HD_ADD SY_HD
+#endif
+
 namespace sylow {
 
 struct Fp2 {
@@ -23,21 +35,21 @@ SY_HD Fp2 fp2_zero() { return Fp2{fp_zero(), fp_zero()}; }
 SY_HD Fp2 fp2_one() { return Fp2{fp_one(), fp_zero()}; }
 SY_HD bool fp2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) & fp_is_zero(a.c1); }
 SY_HD bool fp2_eq(const Fp2& a, const Fp2& b) { return fp_eq(a.c0, b.c0) & fp_eq(a.c1, b.c1); }
-SY_HD Fp2 fp2_add(const Fp2& a, const Fp2& b) { return Fp2{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
-SY_HD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return Fp2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
-SY_HD Fp2 fp2_dbl(const Fp2& a) { return Fp2{fp_dbl(a.c0), fp_dbl(a.c1)}; }
-SY_HD Fp2 fp2_neg(const Fp2& a) { return Fp2{fp_neg(a.c0), fp_neg(a.c1)}; }
-SY_HD Fp2 fp2_mul3(const Fp2& a) { return fp2_add(fp2_dbl(a), a); }
+SY_HD_ADD Fp2 fp2_add(const Fp2& a, const Fp2& b) { return Fp2{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+SY_HD_ADD Fp2 fp2_sub(const Fp2& a, const Fp2& b) { return Fp2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+SY_HD_ADD Fp2 fp2_dbl(const Fp2& a) { return Fp2{fp_dbl(a.c0), fp_dbl(a.c1)}; }
+SY_HD_ADD Fp2 fp2_neg(const Fp2& a) { return Fp2{fp_neg(a.c0), fp_neg(a.c1)}; }
+SY_HD_ADD Fp2 fp2_mul3(const Fp2& a) { return fp2_add(fp2_dbl(a), a); }
 // frobenius(1): the Fp non-residue is -1, so this is conjugation (fp2.rs:119-133)
 SY_HD Fp2 fp2_conj(const Fp2& a) { return Fp2{a.c0, fp_neg(a.c1)}; }
 SY_HD Fp2 fp2_select(bool c, const Fp2& a, const Fp2& b) {
   return Fp2{fp_select(c, a.c0, b.c0), fp_select(c, a.c1, b.c1)};
 }
 // scale(1/2) (pairing.rs:799,805): halving the Montgomery representative halves the value
-SY_HD Fp2 fp2_halve(const Fp2& a) { return Fp2{fp_halve(a.c0), fp_halve(a.c1)}; }
+SY_HD_ADD Fp2 fp2_halve(const Fp2& a) { return Fp2{fp_halve(a.c0), fp_halve(a.c1)}; }
 
 // (a0 + a1 u)(9 + u) = (9 a0 - a1) + (a0 + 9 a1) u    (fp2.rs:99-107)
-SY_HD Fp2 fp2_mul_xi(const Fp2& a) {
+SY_HD_ADD Fp2 fp2_mul_xi(const Fp2& a) {
   Fp t0 = fp_mul9(a.c0), t1 = fp_mul9(a.c1);
   return Fp2{fp_sub(t0, a.c1), fp_add(t1, a.c0)};
 }

@@ -266,3 +266,22 @@ def test_error_paths(eng):
         eng.hash_to_g1_batch([b"x"], dst=b"d" * 300)  # oversize DST not supported yet -> ERR_ARG, not a crash
     assert eng.pairing_batch(np.zeros((0, 64), np.uint8), np.zeros((0, 128), np.uint8)).shape == (0, 384)
     assert eng.launch_count > 0
+
+
+def test_cpp_header(kats, tmp_path):
+    """include/sylow_b200.hpp (the compiled-language host mirror) drives the same C ABI."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_hpp")
+    libdir = os.path.join(root, "sylow_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "cpp", "test_hpp.cpp"), "-o", exe,
+                           "-L" + libdir, "-lsylow_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe], text=True).splitlines()
+    tag = {l.split()[0]: l.split()[1:] for l in out}
+    assert [int(x, 16) for x in tag["GT"]] == [int(x, 16) for x in kats["gt_generator"]["fp12"]]
+    assert tag["IDENT"] == ["1"] and tag["EMPTY"] == ["1"] and tag["BILINEAR"] == ["1"]
+    assert tag["VERIFY"] == ["1", "0", "1"]
+    sig = o.proj_to_affine(o.FpOps, o.sign(0x1234567890ABCDEF, (20).to_bytes(4, "big")))
+    assert int(tag["SIG"][0], 16) == sig[0]
