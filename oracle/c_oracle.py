@@ -182,7 +182,7 @@ def time_pairings(budget_s: float):
     pairing_batch(p, q, threads=c)
     dt = time.perf_counter() - t0
     reps = max(1, int(budget_s / max(dt, 1e-3)) - 1)
-    reps = min(reps, 64)
+    reps = min(reps, 512)
     P, Q = np.tile(p, (reps, 1)), np.tile(q, (reps, 1))
     t0 = time.perf_counter()
     pairing_batch(P, Q, threads=c)

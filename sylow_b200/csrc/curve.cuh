@@ -148,6 +148,7 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul(const Proj<F>& p, const uint32_t* k) {
   for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
   Proj<F> acc = tab[k[7] >> 28];
   for (int w = 62; w >= 0; w--) {
+    SY_LOOP_SYNC();
     acc = proj_double(acc);
     acc = proj_double(acc);
     acc = proj_double(acc);

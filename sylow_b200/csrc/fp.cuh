@@ -31,6 +31,23 @@
   __device__ __constant__ const type name##_d[n] = {__VA_ARGS__}; \
   static const type name##_h[n] = {__VA_ARGS__};
 
+// Optional block-wide re-convergence inside the long loops: keeps the warps of a block in the same
+// region of the (large) instruction stream so instruction-cache lines fetched by one warp are hit by
+// the others.  Only legal when every thread of the block runs the loop (the kernels guarantee it).
+#ifndef SY_BLOCK_SYNC
+#define SY_BLOCK_SYNC 1
+#endif
+#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
+#define SY_LOOP_SYNC() __syncthreads()
+#else
+#define SY_LOOP_SYNC() ((void)0)
+#endif
+#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 2
+#define SY_STEP_SYNC() __syncthreads()
+#else
+#define SY_STEP_SYNC() ((void)0)
+#endif
+
 namespace sylow {
 
 struct Fp {
@@ -377,6 +394,7 @@ SY_HD Fp fp_mul9(const Fp& a) {
 SY_HD_NOINLINE Fp fp_pow(const Fp& a, const uint32_t* e, int top_bit) {
   Fp r = a;
   for (int i = top_bit - 1; i >= 0; i--) {
+    if ((i & 15) == 15) SY_LOOP_SYNC();
     r = fp_sqr(r);
     if ((e[i >> 5] >> (i & 31)) & 1) r = fp_mul(r, a);
   }

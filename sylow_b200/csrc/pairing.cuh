@@ -8,23 +8,6 @@
 #pragma once
 #include "curve.cuh"
 
-// Optional block-wide re-convergence inside the long loops: keeps the warps of a block in the same
-// region of the (large) instruction stream so instruction-cache lines fetched by one warp are hit by
-// the others.  Only legal when every thread of the block runs the loop (the kernels guarantee it).
-#ifndef SY_BLOCK_SYNC
-#define SY_BLOCK_SYNC 1
-#endif
-#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
-#define SY_LOOP_SYNC() __syncthreads()
-#else
-#define SY_LOOP_SYNC() ((void)0)
-#endif
-#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 2
-#define SY_STEP_SYNC() __syncthreads()
-#else
-#define SY_STEP_SYNC() ((void)0)
-#endif
-
 namespace sylow {
 
 struct Ell {

@@ -28,8 +28,8 @@ using namespace sylow;
 #ifndef SY_FEXP_MINB
 #define SY_FEXP_MINB 1
 #endif
-#define SY_MUL_THREADS 128
-#define SY_HASH_THREADS 128
+#define SY_MUL_THREADS 256
+#define SY_HASH_THREADS 256
 #define SY_SMALL_THREADS 128
 
 struct DstPrime {
@@ -108,46 +108,49 @@ k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
   ok[c] = one ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(SY_MUL_THREADS)
+__global__ void __launch_bounds__(SY_MUL_THREADS, 1)
 k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                      const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
                      uint8_t* __restrict__ out_inf) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;  // all threads run the (block-synchronised) loops; surplus is discarded
   G1Aff a{fp_load(pts + i * 64), fp_load(pts + i * 64 + 32), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
   G1Aff r = proj_to_affine(proj_scalar_mul(affine_to_proj(a), k.l));
+  if (i0 >= n) return;
   fp_store(out + i * 64, r.x);
   fp_store(out + i * 64 + 32, r.y);
   if (out_inf) out_inf[i] = r.inf;
 }
 
-__global__ void __launch_bounds__(SY_MUL_THREADS)
+__global__ void __launch_bounds__(SY_MUL_THREADS, 1)
 k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                        const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
                        uint8_t* __restrict__ out_inf) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
   G2Aff a{fp2_load(pts + i * 128), fp2_load(pts + i * 128 + 64), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
   G2Aff r = proj_to_affine(proj_scalar_mul(affine_to_proj(a), k.l));
+  if (i0 >= n) return;
   fp2_store(out + i * 128, r.x);
   fp2_store(out + i * 128 + 64, r.y);
   if (out_inf) out_inf[i] = r.inf;
 }
 
 // out[i] = affine(+-hash_to_curve(msg_i)); status[i] = 1 if the SvdW sqrt check failed
-__global__ void __launch_bounds__(SY_HASH_THREADS)
+__global__ void __launch_bounds__(SY_HASH_THREADS, 1)
 k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
              const __grid_constant__ DstPrime dst, int negate, uint8_t* __restrict__ out,
              uint8_t* __restrict__ out_inf, int* __restrict__ fail_flag) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
   uint64_t o0 = offsets[i], o1 = offsets[i + 1];
   G1Proj p;
   bool ok = hash_to_g1(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, p);
-  if (!ok) atomicExch(fail_flag, 1);
   G1Aff r = proj_to_affine(p);
+  if (i0 >= n) return;
+  if (!ok) atomicExch(fail_flag, 1);
   if (negate && !r.inf) r.y = fp_neg(r.y);
   fp_store(out + i * 64, r.x);
   fp_store(out + i * 64 + 32, r.y);
@@ -155,8 +158,8 @@ k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offs
 }
 
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
   Fp x = fp_load(a + i * 32), y = fp_load(b + i * 32), r;
   switch (op) {
     case 0: r = fp_mul(x, y); break;
@@ -166,13 +169,14 @@ __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, ui
     case 4: r = fp_halve(x); break;
     default: r = fp_neg(x);
   }
+  if (i0 >= n) return;
   fp_store(out + i * 32, r);
 }
 
 __global__ void __launch_bounds__(SY_SMALL_THREADS)
 k_fp12_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
   Fp12 x = fp12_load(a + i * 384), y = fp12_load(b + i * 384), r;
   switch (op) {
     case 0: r = fp12_mul(x, y); break;
@@ -184,6 +188,7 @@ k_fp12_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     case 6: r = cyclotomic_squared(x); break;
     default: r = fp12_sparse_mul(x, y.c0.c0, y.c0.c1, y.c0.c2);
   }
+  if (i0 >= n) return;
   fp12_store(out + i * 384, r);
 }
 
