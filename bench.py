@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20, help="log2 of pairings per GPU per step")
     ap.add_argument("--verify-log2n", type=int, default=18, help="log2 of signatures for the verify_batch leg (0 = skip)")
+    ap.add_argument("--extras", type=int, default=1, help="also time the Groth16-shaped check and scalar-mul configs")
+    ap.add_argument("--groth-log2n", type=int, default=18)
+    ap.add_argument("--mul-log2n", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -310,6 +313,35 @@ def main():
                   "note": "hash-to-curve + 2 Miller loops per signature + product per GPU, all-gather of 384-byte "
                           "partials, one final exponentiation per batch (device-resident inputs)"}
 
+    # ---- further BASELINE configs, as extra keys (device-resident inputs, CUDA events)
+    extras = {}
+    if args.extras:
+        # config #4: Groth16-shaped 4-pair product check, three G2 points fixed across all checks
+        nc = 1 << args.groth_log2n
+        co = eng.g2_precompute(d_g2[:3].cpu().numpy())
+        d_tab = torch.empty(3 * 87 * 192, dtype=torch.uint8, device=dev)
+        eng.tables_to_device(co, d_tab)
+        torch.cuda.synchronize()
+        d_g1c = d_g1[: 4 * nc].contiguous() if 4 * nc <= n else d_g1.repeat((4 * nc + n - 1) // n, 1)[: 4 * nc].contiguous()
+        d_g2c = d_g2[:nc].contiguous()
+        d_ok = torch.empty(nc, dtype=torch.uint8, device=dev)
+        ms_g = time_ms(lambda: eng.pairing_check_fixed_batch_dev(d_g1c, d_g2c, d_tab, 1, 3, d_ok), reps=2)
+        extras["groth16_4pair_checks_per_s"] = world * nc / (max_over_ranks(ms_g) * 1e-3)
+        extras["groth16_checks_per_gpu"] = nc
+        # config #5: variable-base scalar multiplication, 254-bit scalars
+        nm = 1 << args.mul_log2n
+        d_k = torch.from_numpy(rand_scalars(nm)).to(dev)
+        d_p1 = d_g1[:nm].contiguous() if nm <= n else d_g1.repeat((nm + n - 1) // n, 1)[:nm].contiguous()
+        d_p2 = d_g2[:nm].contiguous() if nm <= n else d_g2.repeat((nm + n - 1) // n, 1)[:nm].contiguous()
+        d_o1 = torch.empty((nm, 64), dtype=torch.uint8, device=dev)
+        d_o2 = torch.empty((nm, 128), dtype=torch.uint8, device=dev)
+        ms_1 = time_ms(lambda: eng.g1_mul_batch_dev(d_p1, d_k, d_o1), reps=2)
+        ms_2 = time_ms(lambda: eng.g2_mul_batch_dev(d_p2, d_k, d_o2), reps=2)
+        extras["g1_scalar_muls_per_s"] = world * nm / (max_over_ranks(ms_1) * 1e-3)
+        extras["g2_scalar_muls_per_s"] = world * nm / (max_over_ranks(ms_2) * 1e-3)
+        extras["scalar_muls_per_gpu"] = nm
+        del d_k, d_p1, d_p2, d_o1, d_o2
+
     cpu = None
     if rank == 0 and world == 1:
         v, cores, kind, sample = cpu_pairings_per_s(args.cpu_seconds)
@@ -344,6 +376,8 @@ def main():
             line["cpu_baseline"] = cpu
         if verify:
             line["verify_batch"] = verify
+        if extras:
+            line["other_configs"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

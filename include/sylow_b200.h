@@ -89,6 +89,28 @@ int sylow_b200_fp12_product(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uin
 int sylow_b200_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                                    const uint8_t* g2_inf, size_t pairs_per_check, size_t n_checks, uint8_t* ok_out);
 
+/* ---- precomputed G2 (G2PreComputed) --------------------------------------------------------------- */
+
+/* coeffs_out[i] = G2Affine::precompute(g2[i]) (pairing.rs:676-708): the 87 line-coefficient triples
+ * Ell(c0, c1, c2), 3 x Fp2 = 192 B each, 16704 B per point, canonical, bit-identical to the reference's
+ * G2PreComputed::coeffs. */
+int sylow_b200_g2_precompute(sylow_b200_ctx* ctx, const uint8_t* g2, size_t n, uint8_t* coeffs_out /* n*16704 */);
+
+/* f_out[i] = G2PreComputed::miller_loop(g1[i]) (pairing.rs:590-619) for ONE precomputed G2 point against n G1
+ * points; the table is staged in shared memory and broadcast to the threads.  Infinite G1 gives 1. */
+int sylow_b200_miller_loop_precomputed(sylow_b200_ctx* ctx, const uint8_t* coeffs /* 16704 */, const uint8_t* g1,
+                                       const uint8_t* g1_inf, size_t n, uint8_t* f_out /* n*384 */);
+
+/* Product checks where the LAST k_fixed pairs of every check use the same k_fixed G2 points for all checks
+ * (Groth16: e(A,B) e(-alpha,beta) e(-L,gamma) e(-C,delta) == 1 with beta, gamma, delta fixed).  g1 holds
+ * k_var + k_fixed points per check (variable pairs first), g2_var k_var points per check, coeffs_fixed the
+ * k_fixed tables from sylow_b200_g2_precompute.  One multi-Miller loop with a shared squaring per check
+ * (glued_miller_loop, pairing.rs:970-1022) + one final exponentiation.  Supported shapes (k_var, k_fixed):
+ * (1,1), (1,3), (0,1); anything else returns SYLOW_B200_ERR_ARG (use sylow_b200_pairing_check_batch). */
+int sylow_b200_pairing_check_fixed_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf,
+                                         const uint8_t* g2_var, const uint8_t* g2_var_inf, size_t k_var,
+                                         const uint8_t* coeffs_fixed, size_t k_fixed, size_t n_checks, uint8_t* ok_out);
+
 /* ---- scalar multiplication --------------------------------------------------------------------- */
 
 /* out[i] = affine(scalars[i] * pts[i]);  replaces `&G1Projective * &Fp` + GroupAffine::from
@@ -147,6 +169,14 @@ int sylow_b200_final_exp_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_f, size
 int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
                                        const uint8_t* d_g2, const uint8_t* d_g2_inf, size_t pairs_per_check,
                                        size_t n_checks, uint8_t* d_ok_out, void* stream);
+/* d_tables: k_fixed tables in the library's device form, produced by sylow_b200_tables_to_device. */
+int sylow_b200_pairing_check_fixed_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
+                                             const uint8_t* d_g2_var, const uint8_t* d_g2_var_inf, size_t k_var,
+                                             const uint8_t* d_tables, size_t k_fixed, size_t n_checks,
+                                             uint8_t* d_ok_out, void* stream);
+/* Converts k canonical host tables (sylow_b200_g2_precompute output) to the device form at d_tables_out
+ * (k*16704 B of device memory). */
+int sylow_b200_tables_to_device(sylow_b200_ctx* ctx, const uint8_t* coeffs, size_t k, uint8_t* d_tables_out, void* stream);
 int sylow_b200_g1_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_pts_inf,
                                 const uint8_t* d_scalars, size_t n, uint8_t* d_out, uint8_t* d_out_inf, void* stream);
 int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_pts_inf,

@@ -125,6 +125,57 @@ class Engine:
                                                           n // k, _ptr(ok)), "pairing_check_batch")
         return ok.astype(bool)
 
+    # ------------------------------------------------------------------ precomputed G2
+    def g2_precompute(self, g2) -> np.ndarray:
+        """G2Affine::precompute: (n, 87, 3, 64) uint8 canonical line coefficients."""
+        g2 = _u8(g2, 128, "g2")
+        out = np.empty((g2.shape[0], 87 * 192), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_g2_precompute(self._h, _ptr(g2), g2.shape[0], _ptr(out)), "g2_precompute")
+        return out
+
+    def miller_loop_precomputed(self, coeffs, g1, g1_inf=None) -> np.ndarray:
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint8).reshape(87 * 192)
+        g1 = _u8(g1, 64, "g1")
+        n = g1.shape[0]
+        g1_inf = None if g1_inf is None else np.ascontiguousarray(g1_inf, dtype=np.uint8).reshape(n)
+        out = np.empty((n, 384), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_miller_loop_precomputed(self._h, _ptr(coeffs), _ptr(g1), _ptr(g1_inf), n,
+                                                              _ptr(out)), "miller_loop_precomputed")
+        return out
+
+    def pairing_check_fixed_batch(self, g1, g2_var, coeffs_fixed, k_var: int, k_fixed: int, g1_inf=None,
+                                  g2_var_inf=None) -> np.ndarray:
+        g1 = _u8(g1, 64, "g1")
+        k = k_var + k_fixed
+        if k <= 0 or g1.shape[0] % k:
+            raise ValueError("g1 rows (%d) not a multiple of k_var + k_fixed = %d" % (g1.shape[0], k))
+        n_checks = g1.shape[0] // k
+        g2_var = None if k_var == 0 else _u8(g2_var, 128, "g2_var")
+        if k_var and g2_var.shape[0] != n_checks * k_var:
+            raise ValueError("g2_var must have n_checks * k_var rows")
+        coeffs_fixed = np.ascontiguousarray(coeffs_fixed, dtype=np.uint8).reshape(k_fixed, 87 * 192)
+        g1_inf = None if g1_inf is None else np.ascontiguousarray(g1_inf, dtype=np.uint8).reshape(-1)
+        g2_var_inf = None if g2_var_inf is None else np.ascontiguousarray(g2_var_inf, dtype=np.uint8).reshape(-1)
+        ok = np.empty(n_checks, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_pairing_check_fixed_batch(self._h, _ptr(g1), _ptr(g1_inf), _ptr(g2_var),
+                                                                _ptr(g2_var_inf), k_var, _ptr(coeffs_fixed), k_fixed,
+                                                                n_checks, _ptr(ok)), "pairing_check_fixed_batch")
+        return ok.astype(bool)
+
+    def tables_to_device(self, coeffs_fixed, d_tables):
+        coeffs_fixed = np.ascontiguousarray(coeffs_fixed, dtype=np.uint8).reshape(-1, 87 * 192)
+        self._ck(self._lib.sylow_b200_tables_to_device(self._h, _ptr(coeffs_fixed), coeffs_fixed.shape[0],
+                                                       self._tp(d_tables), self._stream()), "tables_to_device")
+
+    def pairing_check_fixed_batch_dev(self, d_g1, d_g2_var, d_tables, k_var, k_fixed, d_ok, d_g1_inf=None,
+                                      d_g2_var_inf=None):
+        n_checks = d_g1.shape[0] // (k_var + k_fixed)
+        self._ck(self._lib.sylow_b200_pairing_check_fixed_batch_dev(self._h, self._tp(d_g1), self._tp(d_g1_inf),
+                                                                    self._tp(d_g2_var), self._tp(d_g2_var_inf), k_var,
+                                                                    self._tp(d_tables), k_fixed, n_checks,
+                                                                    self._tp(d_ok), self._stream()),
+                 "pairing_check_fixed_batch_dev")
+
     # ------------------------------------------------------------------ scalar multiplication
     def _mul(self, fn, width, pts, scalars, pts_inf):
         pts = _u8(pts, width, "pts")

@@ -88,6 +88,93 @@ SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const
   return f;
 }
 
+// G2Affine::precompute (pairing.rs:676-708): the 87 line-coefficient triples of a fixed G2 point, in
+// the reference's order (64 doublings interleaved with 21 additions, then the two Frobenius additions).
+SY_HD_NOINLINE void g2_precompute(const Fp2& qx, const Fp2& qy, Ell* out) {
+  G2Proj r{qx, qy, fp2_one()};
+  Fp2 nqy = fp2_neg(qy);
+  int idx = 0;
+  for (int i = 0; i < 64; i++) {
+    SY_LOOP_SYNC();
+    out[idx++] = g2_doubling_step(r);
+    int digit = SY_TAB(kAteNaf)[i];
+    if (digit != 0) out[idx++] = g2_addition_step(r, qx, digit > 0 ? qy : nqy);
+  }
+  Fp2 q1x = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(qx));
+  Fp2 q1y = fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(qy));
+  Fp2 q2x = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q1x));
+  Fp2 q2y = fp2_neg(fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q1y)));
+  out[idx++] = g2_addition_step(r, q1x, q1y);
+  out[idx++] = g2_addition_step(r, q2x, q2y);
+}
+
+// One G1 point of a glued loop.  `skip` pairs contribute the identity line (1, 0, 0): f * 1 = f exactly.
+struct MillerG1 {
+  Fp x, y;
+  bool skip;
+};
+SY_HD Fp12 glued_mul_line(const Fp12& f, const Ell& l, const MillerG1& p) {
+  Fp2 l0 = fp2_select(p.skip, fp2_one(), l.c0);
+  Fp2 lvw = fp2_select(p.skip, fp2_zero(), fp2_mul_fp(l.c1, p.y));
+  Fp2 lvv = fp2_select(p.skip, fp2_zero(), fp2_mul_fp(l.c2, p.x));
+  return fp12_sparse_mul(f, l0, lvw, lvv);
+}
+
+// glued_miller_loop (pairing.rs:970-1022) for NV pairs whose G2 point is per-item (line coefficients
+// computed on the fly, fused) followed by NF pairs against fixed, precomputed G2 tables (87 triples each,
+// Montgomery form; on the device they sit in shared memory and every thread reads the same triple).
+// One shared Fp12 squaring per digit for all NV + NF pairs.  The product equals the reference's
+// (multiplication order differs; Fp12 multiplication is exact and commutative).
+template <int NV, int NF>
+SY_HD_NOINLINE Fp12 glued_miller_loop(const MillerG1* p /* NV + NF */, const Fp2* qx, const Fp2* qy /* NV */,
+                                      const Ell* const* tables /* NF */) {
+  G2Proj r[NV > 0 ? NV : 1];
+  Fp2 nqy[NV > 0 ? NV : 1];
+  for (int v = 0; v < NV; v++) {
+    r[v] = G2Proj{qx[v], qy[v], fp2_one()};
+    nqy[v] = fp2_neg(qy[v]);
+  }
+  Fp12 f = fp12_one();
+  int idx = 0;
+  for (int i = 0; i < 64; i++) {
+    SY_LOOP_SYNC();
+    if (i != 0) f = fp12_sqr(f);
+    for (int v = 0; v < NV; v++) {
+      Ell l = g2_doubling_step(r[v]);
+      f = glued_mul_line(f, l, p[v]);
+    }
+    for (int t = 0; t < NF; t++) f = glued_mul_line(f, tables[t][idx], p[NV + t]);
+    idx++;
+    int digit = SY_TAB(kAteNaf)[i];
+    if (digit != 0) {
+      for (int v = 0; v < NV; v++) {
+        Ell l = g2_addition_step(r[v], qx[v], digit > 0 ? qy[v] : nqy[v]);
+        f = glued_mul_line(f, l, p[v]);
+      }
+      for (int t = 0; t < NF; t++) f = glued_mul_line(f, tables[t][idx], p[NV + t]);
+      idx++;
+    }
+  }
+  for (int k = 0; k < 2; k++) {
+    for (int v = 0; v < NV; v++) {
+      // Q1 = psi(Q), then Q2 = -psi(Q1)
+      Fp2 q1x = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(qx[v]));
+      Fp2 q1y = fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(qy[v]));
+      if (k == 1) {
+        Fp2 tx = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q1x));
+        Fp2 ty = fp2_neg(fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q1y)));
+        q1x = tx;
+        q1y = ty;
+      }
+      Ell l = g2_addition_step(r[v], q1x, q1y);
+      f = glued_mul_line(f, l, p[v]);
+    }
+    for (int t = 0; t < NF; t++) f = glued_mul_line(f, tables[t][idx], p[NV + t]);
+    idx++;
+  }
+  return f;
+}
+
 // ---------------------------------------------------------------------------- final exponentiation
 // fp6.rs:203-209 / fp12.rs:515-522 for e in {1, 2, 3}
 SY_HD_NOINLINE Fp12 fp12_frobenius(const Fp12& a, int e) {
@@ -134,16 +221,21 @@ SY_HD_NOINLINE Fp12 cyclotomic_squared(const Fp12& f) {
   return Fp12{Fp6{z0, z4, z3}, Fp6{z2, z1, z5}};
 }
 
-// conj(f^x) with x = BLS_X (pairing.rs:366-392).  The reference walks 256 exponent bits; the
-// leading zero bits only square 1, so starting at bit 62 is exact.
+// conj(f^x) with x = BLS_X (pairing.rs:366-392).  The reference walks 256 exponent bits one at a time; the
+// value f^x is the same for any addition chain, so this uses the width-3 NAF of x (63 digits, 18 of them
+// non-zero, digits +-1, +-3): 62 cyclotomic squarings + 18 multiplications instead of 62 + 27.  Negative
+// digits multiply by the conjugate, which is the inverse on the cyclotomic subgroup f lives in.
 SY_HD_NOINLINE Fp12 exp_by_neg_z(const Fp12& f) {
-  Fp12 res = f;
-  for (int i = 61; i >= 0; i--) {
+  Fp12 f3 = fp12_mul(cyclotomic_squared(f), f);
+  Fp12 res = SY_TAB(kXWnaf3)[0] == 3 ? f3 : f;
+  for (int i = 1; i < SY_XWNAF3_LEN; i++) {
     SY_LOOP_SYNC();
     res = cyclotomic_squared(res);
-    if ((SY_BLS_X >> i) & 1) {
+    int d = SY_TAB(kXWnaf3)[i];
+    if (d != 0) {
       SY_STEP_SYNC();
-      res = fp12_mul(res, f);
+      const Fp12& t = (d == 3 || d == -3) ? f3 : f;
+      res = fp12_mul(res, d > 0 ? t : fp12_conj(t));
     }
   }
   return fp12_conj(res);

@@ -58,6 +58,81 @@ k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, con
     fp12_store(f_out + i * 384, f);
 }
 
+
+// coeffs[i] = G2Affine::precompute(g2[i]): 87 triples (c0, c1, c2), 16704 B per point, Montgomery (raw) or canonical
+__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
+k_g2_precompute(const uint8_t* __restrict__ g2, size_t n, uint8_t* __restrict__ coeffs, int raw_out) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
+  Ell c[87];
+  g2_precompute(fp2_load(g2 + i * 128), fp2_load(g2 + i * 128 + 64), c);
+  if (i0 >= n) return;
+  uint8_t* o = coeffs + i * (87 * 192);
+  for (int j = 0; j < 87; j++) {
+    if (raw_out) {
+      fp2_store_raw(o + 192 * j, c[j].c0);
+      fp2_store_raw(o + 192 * j + 64, c[j].c1);
+      fp2_store_raw(o + 192 * j + 128, c[j].c2);
+    } else {
+      fp2_store(o + 192 * j, c[j].c0);
+      fp2_store(o + 192 * j + 64, c[j].c1);
+      fp2_store(o + 192 * j + 128, c[j].c2);
+    }
+  }
+}
+
+// canonical <-> Montgomery for n Fp values (line-coefficient tables)
+__global__ void k_fp_convert(const uint8_t* in, size_t n, uint8_t* out, int to_mont) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (to_mont)
+    fp_store_raw(out + i * 32, fp_load(in + i * 32));
+  else
+    fp_store(out + i * 32, fp_load_raw(in + i * 32));
+}
+
+// Item i multiplies NV fused pairs (g1v[i*sv + v], g2v[i*NV + v]) and NF pairs against the fixed tables
+// (g1f[i*sf + t], table t): f_out[i] = glued_miller_loop of those NV + NF pairs, Montgomery form.
+// The NF tables (87 * 192 B each, Montgomery form) are staged once per block in shared memory; every
+// thread of a warp then reads the same triple (broadcast, conflict-free).
+template <int NV, int NF>
+__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
+k_glued(const uint8_t* __restrict__ g1v, size_t sv, const uint8_t* __restrict__ g1v_inf, const uint8_t* __restrict__ g2v,
+        const uint8_t* __restrict__ g2v_inf, const uint8_t* __restrict__ g1f, size_t sf,
+        const uint8_t* __restrict__ g1f_inf, const uint8_t* __restrict__ tables, size_t n,
+        uint8_t* __restrict__ f_out) {
+  extern __shared__ uint4 sy_smem[];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(tables);
+    for (int w = threadIdx.x; w < NF * 87 * 12; w += blockDim.x) sy_smem[w] = src[w];
+    __syncthreads();
+  }
+  const Ell* tabs[NF > 0 ? NF : 1];
+  for (int t = 0; t < NF; t++) tabs[t] = reinterpret_cast<const Ell*>(sy_smem) + 87 * t;
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
+  MillerG1 p[NV + NF];
+  Fp2 qx[NV > 0 ? NV : 1], qy[NV > 0 ? NV : 1];
+  for (int v = 0; v < NV; v++) {
+    const uint8_t* a = g1v + (i * sv + v) * 64;
+    const uint8_t* q = g2v + (i * NV + v) * 128;
+    p[v].x = fp_load(a);
+    p[v].y = fp_load(a + 32);
+    p[v].skip = (g1v_inf && g1v_inf[i * sv + v]) || (g2v_inf && g2v_inf[i * NV + v]);
+    qx[v] = fp2_load(q);
+    qy[v] = fp2_load(q + 64);
+  }
+  for (int t = 0; t < NF; t++) {
+    const uint8_t* a = g1f + (i * sf + t) * 64;
+    p[NV + t].x = fp_load(a);
+    p[NV + t].y = fp_load(a + 32);
+    p[NV + t].skip = g1f_inf && g1f_inf[i * sf + t];
+  }
+  Fp12 f = glued_miller_loop<NV, NF>(p, qx, qy, tabs);
+  if (i0 >= n) return;
+  fp12_store_raw(f_out + i * 384, f);
+}
+
 __global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
 k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +349,8 @@ struct sylow_b200_ctx {
   uint64_t launches = 0;
   DevBuf in_a, in_b, in_c, in_d, flag_a, flag_b, out, scratch0, scratch1, scratch2;
   int* d_fail = nullptr;
+  uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
+  DevBuf tables;
 };
 
 static int fail_cuda(sylow_b200_ctx* ctx, cudaError_t e) {
@@ -344,6 +421,8 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->d_fail) cudaFree(ctx->d_fail);
+  if (ctx->d_gen_table) cudaFree(ctx->d_gen_table);
+  if (ctx->tables.p) cudaFree(ctx->tables.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -513,26 +592,60 @@ static const uint64_t kG2GenWords[16] = {
     5541340697920699818ull,  16416156555105522555ull, 5380518976772849807ull,  1353435754470862315ull,
     6173549831154472795ull,  13567992399387660019ull, 17050234209342075797ull, 650358724130500725ull};
 
-// scratch layout for verify: [0, n*64) -H(m_i); then the G2 generator (128 B)
+#define SY_TABLE_BYTES (87 * 192)
+
+}  // extern "C" (templates need C++ linkage)
+
+template <int NV, int NF>
+static int launch_glued(sylow_b200_ctx* ctx, const uint8_t* g1v, size_t sv, const uint8_t* g1v_inf, const uint8_t* g2v,
+                        const uint8_t* g2v_inf, const uint8_t* g1f, size_t sf, const uint8_t* g1f_inf,
+                        const uint8_t* tables, size_t n, uint8_t* f_out, cudaStream_t s) {
+  static bool attr_done = false;  // per instantiation; setting it twice is harmless
+  size_t smem = (size_t)NF * SY_TABLE_BYTES;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_glued<NV, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_glued<NV, NF><<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, smem, s>>>(g1v, sv, g1v_inf, g2v, g2v_inf, g1f, sf,
+                                                                              g1f_inf, tables, n, f_out);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+extern "C" {
+
+// G2PreComputed of the generator, computed on the device once per context
+static int ensure_gen_table(sylow_b200_ctx* ctx, cudaStream_t s) {
+  if (ctx->d_gen_table) return 0;
+  uint8_t* d_gen = nullptr;
+  CK(cudaMalloc(&d_gen, 128));
+  cudaError_t e = cudaMalloc(&ctx->d_gen_table, SY_TABLE_BYTES);
+  if (e != cudaSuccess) {
+    cudaFree(d_gen);
+    ctx->d_gen_table = nullptr;
+    return fail_cuda(ctx, e);
+  }
+  CK(cudaMemcpyAsync(d_gen, kG2GenWords, 128, cudaMemcpyHostToDevice, s));
+  k_g2_precompute<<<1, 32, 0, s>>>(d_gen, 1, ctx->d_gen_table, 1);
+  LAUNCHED(ctx);
+  CK(cudaStreamSynchronize(s));
+  CK(cudaFree(d_gen));
+  return 0;
+}
+
+// f[i] = miller(sig_i, G2gen) * miller(-H(m_i), pk_i) for every signature, Montgomery form, in scratch0:
+// one 2-pair glued loop per thread (shared squaring; the generator's lines come from shared memory).
 static int verify_miller_values(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
                                 const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n, const DstPrime& dp,
                                 cudaStream_t s) {
-  // interleaved Miller values: f[2i] = miller(sig_i, G2gen), f[2i+1] = miller(-H(m_i), pk_i)
-  CKS(reserve(ctx, ctx->scratch0, 2 * n * 384));
-  CKS(reserve(ctx, ctx->scratch2, n * 64 + n + 128 + 64));
+  CKS(ensure_gen_table(ctx, s));
+  CKS(reserve(ctx, ctx->scratch0, n * 384));
+  CKS(reserve(ctx, ctx->scratch2, n * 65 + 64));
   uint8_t* d_hm = ctx->scratch2.p;
   uint8_t* d_hm_inf = d_hm + n * 64;
-  uint8_t* d_gen = d_hm + ((n * 65 + 63) / 64) * 64;
-  CK(cudaMemcpyAsync(d_gen, kG2GenWords, 128, cudaMemcpyHostToDevice, s));
   CKS(hash_launch(ctx, d_msgs, d_offsets, n, dp, 1, d_hm, d_hm_inf, s));
-  // the two halves are written as two planes: [0,n) sig pairs, [n,2n) hash pairs
-  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(d_sigs, nullptr, d_gen, nullptr, 0, n,
-                                                                     ctx->scratch0.p, 1);
-  LAUNCHED(ctx);
-  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(d_hm, d_hm_inf, d_pks, nullptr, 1, n,
-                                                                     ctx->scratch0.p + n * 384, 1);
-  LAUNCHED(ctx);
-  return 0;
+  return launch_glued<1, 1>(ctx, d_hm, 1, d_hm_inf, d_pks, nullptr, d_sigs, 1, nullptr, ctx->d_gen_table, n,
+                            ctx->scratch0.p, s);
 }
 
 int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
@@ -548,8 +661,8 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
     return 0;
   }
   CKS(verify_miller_values(ctx, d_pks, d_msgs, d_offsets, d_sigs, n, dp, s));
-  CKS(reserve(ctx, ctx->scratch1, (2 * n / 4 + 1) * 384));
-  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, 2 * n, d_f_out, 0, s);
+  CKS(reserve(ctx, ctx->scratch1, (n / 4 + 1) * 384));
+  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n, d_f_out, 0, s);
 }
 
 // ------------------------------------------------------------------------------- host variants
@@ -818,16 +931,110 @@ int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_
   CKS(to_dev(ctx, ctx->in_a, pks, n * 128, &dpk));
   CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
   CKS(verify_miller_values(ctx, dpk, dm, dof, dsg, n, dp, ctx->stream));
-  // planes [0,n) and [n,2n): multiply plane-wise (T = n), then one final exp + compare per signature
-  CKS(reserve(ctx, ctx->scratch1, n * 384));
   CKS(reserve(ctx, ctx->out, n));
-  k_fp12_product_strided<<<nblocks(n, SY_SMALL_THREADS), SY_SMALL_THREADS, 0, ctx->stream>>>(ctx->scratch0.p, 2 * n,
-                                                                                           ctx->scratch1.p, n);
-  LAUNCHED(ctx);
-  k_check_products<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(ctx->scratch1.p, 1, n, ctx->out.p);
+  k_check_products<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(ctx->scratch0.p, 1, n, ctx->out.p);
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(ok_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   return check_hash_fail(ctx);
+}
+
+// ------------------------------------------------------------------------------- precomputed G2
+int sylow_b200_g2_precompute(sylow_b200_ctx* ctx, const uint8_t* g2, size_t n, uint8_t* coeffs_out) {
+  ENTER(ctx);
+  if (n && (!g2 || !coeffs_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t* d2;
+  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
+  CKS(reserve(ctx, ctx->out, n * SY_TABLE_BYTES));
+  k_g2_precompute<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, ctx->stream>>>(d2, n, ctx->out.p, 0);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(coeffs_out, ctx->out.p, n * SY_TABLE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+// uploads k canonical tables and converts them to Montgomery form in ctx->tables
+static int tables_to_dev(sylow_b200_ctx* ctx, const uint8_t* coeffs, size_t k) {
+  const uint8_t* dc;
+  CKS(to_dev(ctx, ctx->in_d, coeffs, k * SY_TABLE_BYTES, &dc));
+  CKS(reserve(ctx, ctx->tables, k * SY_TABLE_BYTES));
+  size_t nfp = k * SY_TABLE_BYTES / 32;
+  k_fp_convert<<<nblocks(nfp, 128), 128, 0, ctx->stream>>>(dc, nfp, ctx->tables.p, 1);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_miller_loop_precomputed(sylow_b200_ctx* ctx, const uint8_t* coeffs, const uint8_t* g1,
+                                       const uint8_t* g1_inf, size_t n, uint8_t* f_out) {
+  ENTER(ctx);
+  if (!coeffs || (n && (!g1 || !f_out))) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *d1, *d1i;
+  CKS(tables_to_dev(ctx, coeffs, 1));
+  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  CKS((launch_glued<0, 1>(ctx, nullptr, 0, nullptr, nullptr, nullptr, d1, 1, d1i, ctx->tables.p, n, ctx->out.p,
+                          ctx->stream)));
+  k_fp12_convert<<<nblocks(n, 128), 128, 0, ctx->stream>>>(ctx->out.p, n, ctx->out.p, 0);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(f_out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_pairing_check_fixed_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_g1, const uint8_t* d_g1_inf,
+                                             const uint8_t* d_g2_var, const uint8_t* d_g2_var_inf, size_t k_var,
+                                             const uint8_t* d_tables, size_t k_fixed, size_t n_checks,
+                                             uint8_t* d_ok_out, void* stream) {
+  if (!ctx || (n_checks && (!d_g1 || !d_ok_out || !d_tables || (k_var && !d_g2_var)))) return SYLOW_B200_ERR_ARG;
+  if (!n_checks) return 0;
+  cudaStream_t s = pick(ctx, stream);
+  size_t k = k_var + k_fixed;
+  CKS(reserve(ctx, ctx->scratch0, n_checks * 384));
+  const uint8_t* g1f = d_g1 + k_var * 64;
+  const uint8_t* g1f_inf = d_g1_inf ? d_g1_inf + k_var : nullptr;
+  int st;
+  if (k_var == 1 && k_fixed == 1)
+    st = launch_glued<1, 1>(ctx, d_g1, k, d_g1_inf, d_g2_var, d_g2_var_inf, g1f, k, g1f_inf, d_tables, n_checks, ctx->scratch0.p, s);
+  else if (k_var == 1 && k_fixed == 3)
+    st = launch_glued<1, 3>(ctx, d_g1, k, d_g1_inf, d_g2_var, d_g2_var_inf, g1f, k, g1f_inf, d_tables, n_checks, ctx->scratch0.p, s);
+  else if (k_var == 0 && k_fixed == 1)
+    st = launch_glued<0, 1>(ctx, d_g1, k, d_g1_inf, d_g2_var, d_g2_var_inf, g1f, k, g1f_inf, d_tables, n_checks, ctx->scratch0.p, s);
+  else
+    return SYLOW_B200_ERR_ARG;  // other shapes: use sylow_b200_pairing_check_batch
+  CKS(st);
+  k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, 1, n_checks, d_ok_out);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_tables_to_device(sylow_b200_ctx* ctx, const uint8_t* coeffs, size_t k, uint8_t* d_tables_out, void* stream) {
+  if (!ctx || !coeffs || !d_tables_out || !k) return SYLOW_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CKS(tables_to_dev(ctx, coeffs, k));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(d_tables_out, ctx->tables.p, k * SY_TABLE_BYTES, cudaMemcpyDeviceToDevice, pick(ctx, stream)));
+  return 0;
+}
+
+int sylow_b200_pairing_check_fixed_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf,
+                                         const uint8_t* g2_var, const uint8_t* g2_var_inf, size_t k_var,
+                                         const uint8_t* coeffs_fixed, size_t k_fixed, size_t n_checks, uint8_t* ok_out) {
+  ENTER(ctx);
+  if (n_checks && (!g1 || !ok_out || !coeffs_fixed || (k_var && !g2_var))) return SYLOW_B200_ERR_ARG;
+  if (!((k_var == 1 && (k_fixed == 1 || k_fixed == 3)) || (k_var == 0 && k_fixed == 1))) return SYLOW_B200_ERR_ARG;
+  if (!n_checks) return 0;
+  size_t k = k_var + k_fixed;
+  const uint8_t *d1, *d1i, *d2, *d2i;
+  CKS(tables_to_dev(ctx, coeffs_fixed, k_fixed));
+  CKS(to_dev(ctx, ctx->in_a, g1, n_checks * k * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n_checks * k, &d1i));
+  CKS(to_dev(ctx, ctx->in_b, g2_var, n_checks * k_var * 128, &d2));
+  CKS(to_dev(ctx, ctx->flag_b, g2_var_inf, n_checks * k_var, &d2i));
+  CKS(reserve(ctx, ctx->out, n_checks));
+  CKS(sylow_b200_pairing_check_fixed_batch_dev(ctx, d1, d1i, d2, d2i, k_var, ctx->tables.p, k_fixed, n_checks, ctx->out.p,
+                                               nullptr));
+  CK(cudaMemcpyAsync(ok_out, ctx->out.p, n_checks, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
 }
 
 // ------------------------------------------------------------------------------- diagnostics

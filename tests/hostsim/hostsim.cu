@@ -46,6 +46,32 @@ void hs_miller_loop(const uint8_t* g1, const uint8_t* g2, uint8_t* out) {
   Fp12 f = miller_loop(fp_load(g1), fp_load(g1 + 32), fp2_load(g2), fp2_load(g2 + 64));
   fp12_store(out, f);
 }
+// G2Affine::precompute: 87 triples, canonical, 16704 bytes
+void hs_g2_precompute(const uint8_t* g2, uint8_t* out) {
+  Ell c[87];
+  g2_precompute(fp2_load(g2), fp2_load(g2 + 64), c);
+  for (int i = 0; i < 87; i++) {
+    fp2_store(out + 192 * i, c[i].c0);
+    fp2_store(out + 192 * i + 64, c[i].c1);
+    fp2_store(out + 192 * i + 128, c[i].c2);
+  }
+}
+// glued loop: pair 0 = (g1[0], g2 var) fused, pairs 1..nf = (g1[1+t], fixed[t]) from precomputed tables
+void hs_glued(const uint8_t* g1, const uint8_t* g1_skip, const uint8_t* g2var, const uint8_t* g2fixed, int nv, int nf,
+              uint8_t* out) {
+  MillerG1 p[4];
+  for (int i = 0; i < nv + nf; i++) p[i] = MillerG1{fp_load(g1 + 64 * i), fp_load(g1 + 64 * i + 32), g1_skip[i] != 0};
+  Fp2 qx = fp2_load(g2var), qy = fp2_load(g2var + 64);
+  static Ell tabs[3][87];
+  const Ell* tp[3] = {tabs[0], tabs[1], tabs[2]};
+  for (int t = 0; t < nf; t++) g2_precompute(fp2_load(g2fixed + 128 * t), fp2_load(g2fixed + 128 * t + 64), tabs[t]);
+  Fp12 f;
+  if (nv == 1 && nf == 1) f = glued_miller_loop<1, 1>(p, &qx, &qy, tp);
+  else if (nv == 1 && nf == 3) f = glued_miller_loop<1, 3>(p, &qx, &qy, tp);
+  else if (nv == 0 && nf == 1) f = glued_miller_loop<0, 1>(p, &qx, &qy, tp);
+  else f = glued_miller_loop<1, 0>(p, &qx, &qy, tp);
+  fp12_store(out, f);
+}
 void hs_final_exp(const uint8_t* f, uint8_t* out) { fp12_store(out, final_exponentiation(fp12_load(f))); }
 void hs_pairing(const uint8_t* g1, const uint8_t* g2, uint8_t* out) {
   Fp12 f = miller_loop(fp_load(g1), fp_load(g1 + 32), fp2_load(g2), fp2_load(g2 + 64));

@@ -285,3 +285,65 @@ def test_cpp_header(kats, tmp_path):
     assert tag["VERIFY"] == ["1", "0", "1"]
     sig = o.proj_to_affine(o.FpOps, o.sign(0x1234567890ABCDEF, (20).to_bytes(4, "big")))
     assert int(tag["SIG"][0], 16) == sig[0]
+
+
+def test_g2_precompute_and_precomputed_miller(eng):
+    """G2Affine::precompute coefficients (src/pairing.rs:676-708) and G2PreComputed::miller_loop (:590-619)."""
+    rng = random.Random(18)
+    qs = [o.G2_GEN, w.rand_g2(rng), w.rand_g2(rng)]
+    co = eng.g2_precompute(arr([w.g2_b(q) for q in qs]))
+    for row, q in zip(co, qs):
+        ref = o.g2_precompute(q)
+        b = bytes(row)
+        got = [tuple((w.b_fp(b[192 * i + 64 * j: 192 * i + 64 * j + 32]), w.b_fp(b[192 * i + 64 * j + 32: 192 * i + 64 * j + 64]))
+                     for j in range(3)) for i in range(87)]
+        assert got == [tuple(c) for c in ref]
+    ps = [w.rand_g1(rng) for _ in range(300)]  # more than one block
+    G1 = arr([w.g1_b(p) for p in ps])
+    inf = np.zeros(300, np.uint8)
+    inf[7] = 1
+    out = eng.miller_loop_precomputed(co[1], G1, g1_inf=inf)
+    pre = o.g2_precompute(qs[1])
+    for i in (0, 1, 7, 150, 299):
+        exp = o.FP12_ONE if i == 7 else o.miller_loop(pre, ps[i])
+        assert w.b_fp12(bytes(out[i])) == exp
+    # against the fused path on the whole batch
+    fused = eng.miller_loop_batch(G1, arr([w.g2_b(qs[1])] * 300), g1_inf=inf)
+    assert (out == fused).all()
+
+
+def test_pairing_check_fixed_groth16_shape(eng):
+    """config #4 shape: e(A,B) e(-alpha,beta) e(-L,gamma) e(-C,delta) == 1 with beta, gamma, delta fixed."""
+    rng = random.Random(19)
+    G, Hh = o.affine_to_proj(o.FpOps, o.G1_GEN), o.affine_to_proj(o.Fp2Ops, o.G2_GEN)
+    aff1 = lambda k: o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, G, k % o.R_ORDER))
+    aff2 = lambda k: o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, Hh, k % o.R_ORDER))
+    be, ga, de = (rng.randrange(1, o.R_ORDER) for _ in range(3))
+    fixed = [aff2(be), aff2(ga), aff2(de)]
+    co = eng.g2_precompute(arr([w.g2_b(q) for q in fixed]))
+    g1s, g2v, expect = [], [], []
+    n = 9
+    for t in range(n):
+        a, b_, al, l = (rng.randrange(1, o.R_ORDER) for _ in range(4))
+        # a*b = al*be + l*ga + c*de  (mod r)  -> c
+        c = (a * b_ - al * be - l * ga) * pow(de, -1, o.R_ORDER) % o.R_ORDER
+        if t in (2, 6):
+            c = (c + 1) % o.R_ORDER  # invalid proof
+        g1s += [aff1(a), o.g1_affine_neg(aff1(al)), o.g1_affine_neg(aff1(l)), o.g1_affine_neg(aff1(c))]
+        g2v.append(aff2(b_))
+        expect.append(t not in (2, 6))
+    G1 = arr([w.g1_b(p) for p in g1s])
+    G2v = arr([w.g2_b(q) for q in g2v])
+    got = eng.pairing_check_fixed_batch(G1, G2v, co, 1, 3)
+    assert got.tolist() == expect
+    # same verdicts from the general path and from the oracle's glued_pairing
+    G2all = arr([w.g2_b(q) for t in range(n) for q in [g2v[t]] + fixed])
+    assert eng.pairing_check_batch(G1, G2all, 4).tolist() == expect
+    assert [o.glued_pairing(g1s[4 * t: 4 * t + 4], [g2v[t]] + fixed) == o.FP12_ONE for t in range(3)] == expect[:3]
+    # (1,1) shape with an infinite pair: skipped pairs contribute 1
+    g1 = arr([w.g1_b(g1s[0]), w.g1_b(g1s[1])])
+    inf = np.array([0, 1], np.uint8)
+    r = eng.pairing_check_fixed_batch(g1, G2v[:1], co[:1], 1, 1, g1_inf=inf)
+    assert r.tolist() == [False]
+    with pytest.raises(Exception):
+        eng.pairing_check_fixed_batch(G1[:5], G2v[:1], co[:2], 3, 2)

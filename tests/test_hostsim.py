@@ -140,3 +140,28 @@ def test_keccak_and_hash_to_curve(hs):
         assert [w.b_fp(o64.raw[:32]), w.b_fp(o64.raw[32:])] == o.hash_to_field(m)
         assert hs.hs_hash_to_g1(m, len(m), dst_prime, len(dst_prime), o64) == 0
         assert w.b_g1(o64.raw) == o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m))
+
+
+def test_precompute_and_glued(hs):
+    """G2Affine::precompute coefficients bit-exact (pairing.rs:676-708) and the mixed fused/precomputed glued
+    loop equal to glued_miller_loop (pairing.rs:970-1022)."""
+    rng = random.Random(6)
+    q = w.rand_g2(rng)
+    out = ctypes.create_string_buffer(87 * 192)
+    hs.hs_g2_precompute(w.g2_b(q), out)
+    ref = o.g2_precompute(q)
+    got = [tuple((w.b_fp(out.raw[192 * i + 64 * j: 192 * i + 64 * j + 32]), w.b_fp(out.raw[192 * i + 64 * j + 32: 192 * i + 64 * j + 64]))
+                 for j in range(3)) for i in range(87)]
+    assert got == [tuple(c) for c in ref]
+    f_out = ctypes.create_string_buffer(384)
+    for nv, nf in ((1, 1), (1, 3), (0, 1), (1, 0)):
+        ps = [w.rand_g1(rng) for _ in range(nv + nf)]
+        qv = w.rand_g2(rng)
+        qf = [w.rand_g2(rng) for _ in range(nf)]
+        for skip in ([0] * (nv + nf), [0] * (nv + nf - 1) + [1]):
+            hs.hs_glued(b"".join(w.g1_b(p) for p in ps), bytes(skip), w.g2_b(qv), b"".join(w.g2_b(x) for x in qf) or b"\0",
+                        nv, nf, f_out)
+            qs = ([qv] if nv else []) + qf
+            keep = [i for i in range(nv + nf) if not skip[i]]
+            exp = o.glued_miller_loop([o.g2_precompute(qs[i]) for i in keep], [ps[i] for i in keep])
+            assert w.b_fp12(f_out.raw) == exp, (nv, nf, skip)

@@ -5,7 +5,7 @@ tail -5 gpurun_out/pytest_gpu.log
 timeout 1200 python bench.py > gpurun_out/bench_full.log 2>&1; echo "bench exit $?"
 tail -3 gpurun_out/bench_full.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
-   python bench.py --log2n 17 --steps 2 --warmup 3 --verify-log2n 12 --cpu-seconds 1 > gpurun_out/bench_ncu_list.log 2>&1; echo "ncu list exit $?"
+   python bench.py --log2n 17 --steps 2 --warmup 3 --verify-log2n 12 --extras 0 --cpu-seconds 1 > gpurun_out/bench_ncu_list.log 2>&1; echo "ncu list exit $?"
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_miller|k_final_exp' -s 2 -c 2 -o gpurun_out/prof_r1 -f \
    python bench.py --log2n 17 --steps 1 --warmup 3 --verify-log2n 0 --cpu-seconds 1 > gpurun_out/bench_ncu_full.log 2>&1; echo "ncu full exit $?"
 ls -la gpurun_out
