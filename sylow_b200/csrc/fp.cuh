@@ -66,6 +66,7 @@ struct Fp {
 #define SY_STR2(x) #x
 #define SY_STR(x) SY_STR2(x)
 #define SY_INV 0xe4866389u  // -p^{-1} mod 2^32
+#define SY_INV_ASM 0xe4866389
 
 SY_DEFINE_TABLE(uint32_t, kP, 8, SY_P0, SY_P1, SY_P2, SY_P3, SY_P4, SY_P5, SY_P6, SY_P7)
 
@@ -371,6 +372,292 @@ inline Fp fp_mul(const Fp& a, const Fp& b) {
   for (int i = 0; i < 8; i++) r.l[i] = t[i];
   fp_final_sub(r.l);
   return r;
+}
+#endif
+
+// ---- lazy reduction: full 512-bit products and a separate Montgomery reduction ----------------------
+// fp_mul_wide: T = a * b as 16 plain limbs (64 IMAD.WIDE).  fp_redc_wide: T * R^-1 mod p for T < p * R
+// (72 IMAD).  An Fp2 product needs 3 wide products and only 2 reductions (tower.cuh), 336 IMAD-pipe
+// instructions instead of 3 * 136.  Inputs of fp_mul_wide may be unreduced sums (< 2^256).
+#if defined(__CUDA_ARCH__)
+// X[0..7] += (a0,a1,a2,a3) * b at limb pairs (0,1),(2,3),(4,5),(6,7); carry out is WRITTEN to X[8]
+__device__ __forceinline__ void wide_row_carry(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "=r"(X[8])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+// X[0..6] += ..., X[7] is fresh (written): the top product's high half plus the final carry
+__device__ __forceinline__ void wide_row_fresh(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.hi.u32 %7, %11, %12, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "=r"(X[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+__device__ __forceinline__ void wide_row_first(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+  asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
+      : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+}
+
+// T = a * b.  E collects the products whose position i+j is even, O (offset by one limb) the others;
+// the row order guarantees that every chain either ends in a fresh limb or hands its carry to one.
+__device__ __forceinline__ void fp_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  uint32_t E[16], O[16];
+  O[15] = 0;
+  wide_row_first(E, a[0], a[2], a[4], a[6], b[0]);
+  wide_row_first(O, a[1], a[3], a[5], a[7], b[0]);
+  // row 1: a_even * b1 -> O[0..7] (+carry to O[8]); a_odd * b1 -> E[2..9] (E[8] = 0 so far, E[9] fresh)
+  wide_row_carry(O + 0, a[0], a[2], a[4], a[6], b[1]);
+  E[8] = 0;
+  wide_row_fresh(E + 2, a[1], a[3], a[5], a[7], b[1]);
+#pragma unroll
+  for (int i = 2; i < 8; i += 2) {
+    // even row i: a_even -> E[i..i+7] (+carry to E[i+8]); a_odd -> O[i..i+7] (O[i+6] holds a carry, O[i+7] fresh)
+    wide_row_carry(E + i, a[0], a[2], a[4], a[6], b[i]);
+    wide_row_fresh(O + i, a[1], a[3], a[5], a[7], b[i]);
+    // odd row i+1: a_even -> O[i..i+7] (+carry to O[i+8]); a_odd -> E[i+2..i+9] (E[i+8] holds a carry, E[i+9] fresh)
+    wide_row_carry(O + i, a[0], a[2], a[4], a[6], b[i + 1]);
+    wide_row_fresh(E + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);
+  }
+  // T = E + (O << 32); O[15] = 0 and the sum is < 2^512
+  T[0] = E[0];
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;"
+      : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9]),
+        "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]),
+        "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]),
+        "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]),
+        "r"(O[13]), "r"(O[14]));
+}
+
+// One reduce-only CIOS round (mont_round without the a * b_i terms): T = X + Y * 2^32, X[0] -> 0, roles swap.
+template <bool FIRST>
+__device__ __forceinline__ void redc_round(uint32_t* X, uint32_t* Y) {
+  uint32_t m;
+  if (FIRST) {
+    m = X[0] * SY_INV;
+    asm("mul.lo.u32 %0, %8, " SY_STR(SY_P1) "; mul.hi.u32 %1, %8, " SY_STR(SY_P1) ";\n\t"
+        "mul.lo.u32 %2, %8, " SY_STR(SY_P3) "; mul.hi.u32 %3, %8, " SY_STR(SY_P3) ";\n\t"
+        "mul.lo.u32 %4, %8, " SY_STR(SY_P5) "; mul.hi.u32 %5, %8, " SY_STR(SY_P5) ";\n\t"
+        "mul.lo.u32 %6, %8, " SY_STR(SY_P7) "; mul.hi.u32 %7, %8, " SY_STR(SY_P7) ";"
+        : "=r"(Y[0]), "=r"(Y[1]), "=r"(Y[2]), "=r"(Y[3]), "=r"(Y[4]), "=r"(Y[5]), "=r"(Y[6]), "=r"(Y[7])
+        : "r"(m));
+  } else {
+    // X[0] += Y[1]; m = X[0] * inv; Y = (Y >> 64) + m * p_odd   (the fold carry feeds the chain)
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "mul.lo.u32 %9, %0, " SY_STR(SY_INV_ASM) ";\n\t"
+        "madc.lo.cc.u32 %1, %9, " SY_STR(SY_P1) ", %3;\n\t"
+        "madc.hi.cc.u32 %2, %9, " SY_STR(SY_P1) ", %4;\n\t"
+        "madc.lo.cc.u32 %3, %9, " SY_STR(SY_P3) ", %5;\n\t"
+        "madc.hi.cc.u32 %4, %9, " SY_STR(SY_P3) ", %6;\n\t"
+        "madc.lo.cc.u32 %5, %9, " SY_STR(SY_P5) ", %7;\n\t"
+        "madc.hi.cc.u32 %6, %9, " SY_STR(SY_P5) ", %8;\n\t"
+        "madc.lo.cc.u32 %7, %9, " SY_STR(SY_P7) ", 0;\n\t"
+        "madc.hi.u32 %8, %9, " SY_STR(SY_P7) ", 0;"
+        : "+r"(X[0]), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]),
+          "=&r"(m));
+  }
+  asm("mad.lo.cc.u32 %0, %9, " SY_STR(SY_P0) ", %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, " SY_STR(SY_P0) ", %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, " SY_STR(SY_P2) ", %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, " SY_STR(SY_P2) ", %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, " SY_STR(SY_P4) ", %4;\n\t"
+      "madc.hi.cc.u32 %5, %9, " SY_STR(SY_P4) ", %5;\n\t"
+      "madc.lo.cc.u32 %6, %9, " SY_STR(SY_P6) ", %6;\n\t"
+      "madc.hi.cc.u32 %7, %9, " SY_STR(SY_P6) ", %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7])
+      : "r"(m));
+}
+
+// r = T * R^-1 mod p, fully reduced, for T < p * R.  The 8 rounds work on the low half only:
+// (T_lo + M p) / R <= p, and the high half (< p) is added at the end.
+__device__ __forceinline__ Fp fp_redc_wide(const uint32_t* T) {
+  uint32_t ev[8], od[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) ev[i] = T[i];
+  redc_round<true>(ev, od);
+  redc_round<false>(od, ev);
+  redc_round<false>(ev, od);
+  redc_round<false>(od, ev);
+  redc_round<false>(ev, od);
+  redc_round<false>(od, ev);
+  redc_round<false>(ev, od);
+  redc_round<false>(od, ev);
+  // last round: X = od, Y = ev  ->  W = ev + (od >> 32); r = W + T_hi
+  Fp w, r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=r"(w.l[0]), "=r"(w.l[1]), "=r"(w.l[2]), "=r"(w.l[3]), "=r"(w.l[4]), "=r"(w.l[5]), "=r"(w.l[6]), "=r"(w.l[7])
+      : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+      : "r"(w.l[0]), "r"(w.l[1]), "r"(w.l[2]), "r"(w.l[3]), "r"(w.l[4]), "r"(w.l[5]), "r"(w.l[6]), "r"(w.l[7]),
+        "r"(T[8]), "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+  fp_final_sub(r.l);  // W <= p, T_hi < p  ->  r < 2p
+  return r;
+}
+
+// 16-limb a -= b; returns 0xffffffff if the subtraction borrowed (a < b), else 0
+__device__ __forceinline__ uint32_t wide_sub(uint32_t* a, const uint32_t* b) {
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %0, %17;\n\t"
+      "subc.cc.u32 %1, %1, %18;\n\t"
+      "subc.cc.u32 %2, %2, %19;\n\t"
+      "subc.cc.u32 %3, %3, %20;\n\t"
+      "subc.cc.u32 %4, %4, %21;\n\t"
+      "subc.cc.u32 %5, %5, %22;\n\t"
+      "subc.cc.u32 %6, %6, %23;\n\t"
+      "subc.cc.u32 %7, %7, %24;\n\t"
+      "subc.cc.u32 %8, %8, %25;\n\t"
+      "subc.cc.u32 %9, %9, %26;\n\t"
+      "subc.cc.u32 %10, %10, %27;\n\t"
+      "subc.cc.u32 %11, %11, %28;\n\t"
+      "subc.cc.u32 %12, %12, %29;\n\t"
+      "subc.cc.u32 %13, %13, %30;\n\t"
+      "subc.cc.u32 %14, %14, %31;\n\t"
+      "subc.cc.u32 %15, %15, %32;\n\t"
+      "subc.u32 %16, 0, 0;"
+      : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+        "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "=r"(borrow)
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
+        "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+  return borrow;
+}
+// a[8..15] += p & mask   (adds p * R to the 512-bit value when mask = 0xffffffff)
+__device__ __forceinline__ void wide_add_pR(uint32_t* a, uint32_t mask) {
+  asm("add.cc.u32 %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32 %7, %7, %15;"
+      : "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+      : "r"(mask & SY_P0), "r"(mask & SY_P1), "r"(mask & SY_P2), "r"(mask & SY_P3), "r"(mask & SY_P4),
+        "r"(mask & SY_P5), "r"(mask & SY_P6), "r"(mask & SY_P7));
+}
+// r = a + b without reduction (caller guarantees a + b < 2^256)
+__device__ __forceinline__ void fp_add_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+#else
+// host simulation only: same contracts with 64-bit temporaries
+inline void fp_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+  for (int i = 0; i < 16; i++) T[i] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)a[j] * b[i] + T[i + j];
+      T[i + j] = (uint32_t)c;
+      c >>= 32;
+    }
+    T[i + 8] = (uint32_t)c;
+  }
+}
+inline Fp fp_redc_wide(const uint32_t* T0) {
+  uint32_t T[17];
+  for (int i = 0; i < 16; i++) T[i] = T0[i];
+  T[16] = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t m = T[i] * SY_INV;
+    uint64_t c = 0;
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)m * kP_h[j] + T[i + j];
+      T[i + j] = (uint32_t)c;
+      c >>= 32;
+    }
+    for (int j = i + 8; j < 17 && c; j++) {
+      c += T[j];
+      T[j] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+  Fp r;
+  for (int i = 0; i < 8; i++) r.l[i] = T[8 + i];
+  fp_final_sub(r.l);
+  return r;
+}
+inline uint32_t wide_sub(uint32_t* a, const uint32_t* b) {
+  int64_t bw = 0;
+  for (int i = 0; i < 16; i++) {
+    int64_t d = (int64_t)a[i] - (int64_t)b[i] + bw;
+    a[i] = (uint32_t)d;
+    bw = d >> 32;
+  }
+  return (uint32_t)bw;
+}
+inline void wide_add_pR(uint32_t* a, uint32_t mask) {
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a[8 + i] + (mask & kP_h[i]);
+    a[8 + i] = (uint32_t)c;
+    c >>= 32;
+  }
+}
+inline void fp_add_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)a[i] + b[i];
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
 }
 #endif
 

@@ -9,6 +9,9 @@
 // SY_SMALL_CODE=1 keeps the cheap Fp2 operations (add/sub/double/negate/halve/xi) out of line too, which
 // shrinks the hot instruction footprint of the pairing kernels several-fold (profiles/: the dominant
 // stall of the fully inlined build was instruction fetch).
+#ifndef SY_LAZY_FP2
+#define SY_LAZY_FP2 1
+#endif
 #ifndef SY_SMALL_CODE
 #define SY_SMALL_CODE 0
 #endif
@@ -54,12 +57,33 @@ SY_HD_ADD Fp2 fp2_mul_xi(const Fp2& a) {
   return Fp2{fp_sub(t0, a.c1), fp_add(t1, a.c0)};
 }
 
-// Karatsuba: 3 Fp products (value-equal to the schoolbook of fp2.rs:302-305)
+// Karatsuba with lazy reduction: 3 full 512-bit products, the linear combinations on the unreduced
+// values, and only 2 Montgomery reductions (value-equal to the schoolbook of fp2.rs:302-305).
+//   c0 = a0 b0 - a1 b1            in (-p^2, p^2): add p*R when negative, then < p*R
+//   c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0   in [0, 2 p^2) subset [0, p*R)
+// The sums a0+a1, b0+b1 are NOT reduced (< 2p < 2^255, product < 4 p^2 < 2^510).
 SY_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+#if SY_LAZY_FP2
+  uint32_t t0[16], t1[16], t2[16], sa[8], sb[8];
+  fp_mul_wide(t0, a.c0.l, b.c0.l);
+  fp_mul_wide(t1, a.c1.l, b.c1.l);
+  fp_add_nr(sa, a.c0.l, a.c1.l);
+  fp_add_nr(sb, b.c0.l, b.c1.l);
+  fp_mul_wide(t2, sa, sb);
+  wide_sub(t2, t0);
+  wide_sub(t2, t1);
+  uint32_t neg = wide_sub(t0, t1);
+  wide_add_pR(t0, neg);
+  Fp2 r;
+  r.c0 = fp_redc_wide(t0);
+  r.c1 = fp_redc_wide(t2);
+  return r;
+#else
   Fp t0 = fp_mul(a.c0, b.c0);
   Fp t1 = fp_mul(a.c1, b.c1);
   Fp s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
   return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(s, t0), t1)};
+#endif
 }
 
 // fp2.rs:164-171
