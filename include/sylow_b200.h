@@ -111,6 +111,18 @@ int sylow_b200_pairing_check_fixed_batch(sylow_b200_ctx* ctx, const uint8_t* g1,
                                          const uint8_t* g2_var, const uint8_t* g2_var_inf, size_t k_var,
                                          const uint8_t* coeffs_fixed, size_t k_fixed, size_t n_checks, uint8_t* ok_out);
 
+/* ---- input validation (untrusted batches: precompile calldata, aggregated signatures) ------------- */
+
+/* status_out[i] = 0 if g1[i] is a valid point, SYLOW_B200_ERR_DECODE if a coordinate is >= p
+ * (Fp::from_be_bytes' range check, fp.rs:686-719), SYLOW_B200_ERR_NOT_ON_CURVE if y^2 != x^3 + 3
+ * (G1Affine::new, g1.rs:111-132).  Flagged-infinite points are valid.  The call itself returns 0. */
+int sylow_b200_g1_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, size_t n,
+                                 int8_t* status_out);
+/* As above for G2 plus SYLOW_B200_ERR_NOT_IN_SUBGROUP when (x+1)Q + psi(xQ) + psi^2(xQ) != psi^3(2xQ)
+ * (G2Affine::new_unchecked g2.rs:279-297, G2Projective::new g2.rs:460-525). */
+int sylow_b200_g2_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const uint8_t* g2_inf, size_t n,
+                                 int8_t* status_out);
+
 /* ---- scalar multiplication --------------------------------------------------------------------- */
 
 /* out[i] = affine(scalars[i] * pts[i]);  replaces `&G1Projective * &Fp` + GroupAffine::from

@@ -878,3 +878,49 @@ def verify_batch(pks_affine, msgs, sigs_affine) -> bool:
         g1s += [s, g1_affine_neg(hm)]
         g2s += [G2_GEN, pk]
     return glued_pairing(g1s, g2s) == FP12_ONE
+
+
+# ----------------------------------------------------------------------------------------------
+# input validation                       src/groups/g1.rs:111-132, g2.rs:279-297,460-525
+# ----------------------------------------------------------------------------------------------
+def g1_affine_new(x: int, y: int) -> str:
+    """G1Affine::new: 'ok' or 'NotOnCurve' (every curve point is in the r-torsion), g1.rs:111-132."""
+    return "ok" if (y * y - x * x * x) % P == 3 else "NotOnCurve"
+
+
+def g2_proj_endomorphism(pt):
+    """G2Projective::endomorphism goes through affine coordinates, g2.rs:207-210."""
+    return affine_to_proj(Fp2Ops, g2_endomorphism(proj_to_affine(Fp2Ops, pt)))
+
+
+def g2_projective_new(x, y, z=FP2_ONE) -> str:
+    """G2Projective::new: curve check then the subgroup relation
+    (x+1)Q + psi(xQ) + psi^2(xQ) == psi^3(2xQ), g2.rs:460-525."""
+    lhs = fp2_mul(fp2_sqr(y), z)
+    rhs = fp2_add(fp2_mul(fp2_sqr(x), x), fp2_mul(fp2_mul(fp2_sqr(z), z), FP2_TWIST_CURVE_CONSTANT))
+    if not (lhs == rhs or z == FP2_ZERO):
+        return "NotOnCurve"
+    tmp = (x, y, z)
+    a = proj_mul(Fp2Ops, tmp, BLS_X)
+    b = g2_proj_endomorphism(a)
+    a = proj_add(Fp2Ops, a, tmp)
+    rhs_ = g2_proj_endomorphism(b)
+    lhs_ = proj_add(Fp2Ops, proj_add(Fp2Ops, rhs_, b), a)
+    rhs_ = proj_add(Fp2Ops, proj_double(Fp2Ops, g2_proj_endomorphism(rhs_)), proj_neg(Fp2Ops, lhs_))
+    return "ok" if Fp2Ops.is_zero(rhs_[2]) else "NotInSubgroup"
+
+
+def fp2_sqrt(a):
+    """Square root in Fp2 for p = 3 mod 4 (complex method); None if a is not a square.  Test helper for
+    building points of E'(Fp2) outside the r-torsion (the reference's own Fp2::sqrt is off the path, Q2)."""
+    if a == FP2_ZERO:
+        return FP2_ZERO
+    a1 = fp2_pow(a, (P - 3) // 4)
+    alpha = fp2_mul(fp2_mul(a1, a1), a)
+    x0 = fp2_mul(a1, a)
+    if alpha == (P - 1, 0):
+        r = fp2_mul((0, 1), x0)
+    else:
+        b = fp2_pow(fp2_add(FP2_ONE, alpha), (P - 1) // 2)
+        r = fp2_mul(b, x0)
+    return r if fp2_sqr(r) == a else None

@@ -33,6 +33,8 @@ _SIGNATURES = {
     "sylow_b200_pairing_check_fixed_batch": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_size_t, _P]),
     "sylow_b200_pairing_check_fixed_batch_dev": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_size_t, _P, _P]),
     "sylow_b200_tables_to_device": (c_int, [_P, _P, c_size_t, _P, _P]),
+    "sylow_b200_g1_validate_batch": (c_int, [_P, _P, _P, c_size_t, _P]),
+    "sylow_b200_g2_validate_batch": (c_int, [_P, _P, _P, c_size_t, _P]),
     "sylow_b200_g1_mul_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_g2_mul_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_hash_to_g1_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P]),

@@ -176,6 +176,25 @@ class Engine:
                                                                     self._tp(d_ok), self._stream()),
                  "pairing_check_fixed_batch_dev")
 
+    # ------------------------------------------------------------------ validation
+    def g1_validate_batch(self, g1, g1_inf=None) -> np.ndarray:
+        """int8 status per point: 0 ok, ERR_DECODE, ERR_NOT_ON_CURVE (G1Affine::new)."""
+        g1 = _u8(g1, 64, "g1")
+        n = g1.shape[0]
+        g1_inf = None if g1_inf is None else np.ascontiguousarray(g1_inf, dtype=np.uint8).reshape(n)
+        st = np.empty(n, dtype=np.int8)
+        self._ck(self._lib.sylow_b200_g1_validate_batch(self._h, _ptr(g1), _ptr(g1_inf), n, _ptr(st)), "g1_validate_batch")
+        return st
+
+    def g2_validate_batch(self, g2, g2_inf=None) -> np.ndarray:
+        """int8 status per point: 0 ok, ERR_DECODE, ERR_NOT_ON_CURVE, ERR_NOT_IN_SUBGROUP (G2Projective::new)."""
+        g2 = _u8(g2, 128, "g2")
+        n = g2.shape[0]
+        g2_inf = None if g2_inf is None else np.ascontiguousarray(g2_inf, dtype=np.uint8).reshape(n)
+        st = np.empty(n, dtype=np.int8)
+        self._ck(self._lib.sylow_b200_g2_validate_batch(self._h, _ptr(g2), _ptr(g2_inf), n, _ptr(st)), "g2_validate_batch")
+        return st
+
     # ------------------------------------------------------------------ scalar multiplication
     def _mul(self, fn, width, pts, scalars, pts_inf):
         pts = _u8(pts, width, "pts")

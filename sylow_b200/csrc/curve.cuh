@@ -169,4 +169,39 @@ SY_HD bool g2_on_curve(const Fp2& x, const Fp2& y) {
   return fp2_eq(fp2_sqr(y), rhs);
 }
 
+
+// ---- input validation ------------------------------------------------------------
+// psi on a projective point: (eps0 * conj(x), eps1 * conj(y), conj(z)) - the same point the reference
+// reaches through affine coordinates (g2.rs:140-152, :207-210).
+SY_HD G2Proj g2_psi(const G2Proj& q) {
+  return G2Proj{fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q.x)), fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q.y)), fp2_conj(q.z)};
+}
+// cross-multiplied projective equality (group.rs:426-447)
+SY_HD bool g2_proj_eq(const G2Proj& a, const G2Proj& b) {
+  bool az = fp2_is_zero(a.z), bz = fp2_is_zero(b.z);
+  bool same = fp2_eq(fp2_mul(a.x, b.z), fp2_mul(b.x, a.z)) & fp2_eq(fp2_mul(a.y, b.z), fp2_mul(b.y, a.z));
+  return (az & bz) | (!az & !bz & same);
+}
+// [x]Q for the BN parameter x (63 bits, compile-time constant: uniform control flow)
+SY_HD_NOINLINE G2Proj g2_mul_by_x(const G2Proj& q) {
+  G2Proj acc = q;
+  for (int i = 61; i >= 0; i--) {
+    SY_LOOP_SYNC();
+    acc = proj_double(acc);
+    if ((SY_BLS_X >> i) & 1) acc = proj_add(acc, q);
+  }
+  return acc;
+}
+// G2Projective::new's subgroup relation (g2.rs:460-525): (x+1)Q + psi(xQ) + psi^2(xQ) == psi^3(2xQ)
+SY_HD_NOINLINE bool g2_in_subgroup(const Fp2& x, const Fp2& y) {
+  G2Proj q{x, y, fp2_one()};
+  G2Proj a = g2_mul_by_x(q);
+  G2Proj b = g2_psi(a);
+  a = proj_add(a, q);
+  G2Proj c = g2_psi(b);
+  G2Proj lhs = proj_add(proj_add(c, b), a);
+  G2Proj rhs = proj_double(g2_psi(c));
+  return g2_proj_eq(lhs, rhs);
+}
+
 }  // namespace sylow

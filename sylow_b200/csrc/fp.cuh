@@ -597,8 +597,40 @@ __device__ __forceinline__ void fp_add_nr(uint32_t* r, const uint32_t* a, const 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
         "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
 }
+// r = a - b without correction (caller guarantees a >= b)
+__device__ __forceinline__ void fp_sub_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+}
+// 16-limb a <<= 1 (caller guarantees no overflow)
+__device__ __forceinline__ void wide_dbl(uint32_t* a) {
+#pragma unroll
+  for (int i = 15; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
+  a[0] <<= 1;
+}
 #else
 // host simulation only: same contracts with 64-bit temporaries
+inline void fp_sub_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    int64_t d = (int64_t)a[i] - (int64_t)b[i] + bw;
+    r[i] = (uint32_t)d;
+    bw = d >> 32;
+  }
+}
+inline void wide_dbl(uint32_t* a) {
+  for (int i = 15; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 31);
+  a[0] <<= 1;
+}
 inline void fp_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
   for (int i = 0; i < 16; i++) T[i] = 0;
   for (int i = 0; i < 8; i++) {

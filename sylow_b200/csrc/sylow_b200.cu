@@ -232,6 +232,47 @@ k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offs
   if (out_inf) out_inf[i] = r.inf;
 }
 
+
+// status[i]: 0 ok, SYLOW_B200_ERR_DECODE (a coordinate >= p), SYLOW_B200_ERR_NOT_ON_CURVE   (g1.rs:111-132)
+__global__ void k_g1_validate(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ inf, size_t n,
+                              int8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp xr = fp_load_raw(g1 + i * 64), yr = fp_load_raw(g1 + i * 64 + 32);
+  int8_t st = 0;
+  if (!(inf && inf[i])) {
+    if (!fp_raw_is_canonical(xr) || !fp_raw_is_canonical(yr))
+      st = SYLOW_B200_ERR_DECODE;
+    else if (!g1_on_curve(fp_to_mont(xr), fp_to_mont(yr)))
+      st = SYLOW_B200_ERR_NOT_ON_CURVE;
+  }
+  status[i] = st;
+}
+
+// + SYLOW_B200_ERR_NOT_IN_SUBGROUP: (x+1)Q + psi(xQ) + psi^2(xQ) != psi^3(2xQ)   (g2.rs:279-297, :460-525)
+__global__ void __launch_bounds__(SY_MUL_THREADS, 1)
+k_g2_validate(const uint8_t* __restrict__ g2, const uint8_t* __restrict__ inf, size_t n, int8_t* __restrict__ status) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
+  Fp2 xr = fp2_load_raw(g2 + i * 128), yr = fp2_load_raw(g2 + i * 128 + 64);
+  bool canon = fp_raw_is_canonical(xr.c0) & fp_raw_is_canonical(xr.c1) & fp_raw_is_canonical(yr.c0) &
+               fp_raw_is_canonical(yr.c1);
+  Fp2 x{fp_to_mont(xr.c0), fp_to_mont(xr.c1)}, y{fp_to_mont(yr.c0), fp_to_mont(yr.c1)};
+  bool on = g2_on_curve(x, y);
+  bool sub = g2_in_subgroup(x, y);  // every thread runs the (block-synchronised) ladder
+  if (i0 >= n) return;
+  int8_t st = 0;
+  if (!(inf && inf[i])) {
+    if (!canon)
+      st = SYLOW_B200_ERR_DECODE;
+    else if (!on)
+      st = SYLOW_B200_ERR_NOT_ON_CURVE;
+    else if (!sub)
+      st = SYLOW_B200_ERR_NOT_IN_SUBGROUP;
+  }
+  status[i] = st;
+}
+
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
@@ -1034,6 +1075,38 @@ int sylow_b200_pairing_check_fixed_batch(sylow_b200_ctx* ctx, const uint8_t* g1,
   CKS(sylow_b200_pairing_check_fixed_batch_dev(ctx, d1, d1i, d2, d2i, k_var, ctx->tables.p, k_fixed, n_checks, ctx->out.p,
                                                nullptr));
   CK(cudaMemcpyAsync(ok_out, ctx->out.p, n_checks, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------- validation
+int sylow_b200_g1_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, size_t n,
+                                 int8_t* status_out) {
+  ENTER(ctx);
+  if (n && (!g1 || !status_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *d1, *d1i;
+  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(reserve(ctx, ctx->out, n));
+  k_g1_validate<<<nblocks(n, 128), 128, 0, ctx->stream>>>(d1, d1i, n, reinterpret_cast<int8_t*>(ctx->out.p));
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(status_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_g2_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const uint8_t* g2_inf, size_t n,
+                                 int8_t* status_out) {
+  ENTER(ctx);
+  if (n && (!g2 || !status_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *d2, *d2i;
+  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
+  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
+  CKS(reserve(ctx, ctx->out, n));
+  k_g2_validate<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, ctx->stream>>>(d2, d2i, n,
+                                                                               reinterpret_cast<int8_t*>(ctx->out.p));
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(status_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
 }
 

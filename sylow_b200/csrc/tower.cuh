@@ -86,11 +86,29 @@ SY_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
 #endif
 }
 
-// fp2.rs:164-171
+// fp2.rs:164-171: ((a0+a1)(a0-a1), 2 a0 a1).  The factors a0+a1 and a0-a1+p are left unreduced
+// (< 2p each, product < 4p^2 < p*R, which is all fp_mul needs) and 2 a0 a1 is doubled before its single
+// reduction (2 a0 a1 < 2p^2 < p*R).
 SY_HD_NOINLINE Fp2 fp2_sqr(const Fp2& a) {
+#if SY_LAZY_FP2
+  Fp s, d, pp;
+#pragma unroll
+  for (int i = 0; i < 8; i++) pp.l[i] = SY_TAB(kP)[i];
+  fp_add_nr(s.l, a.c0.l, a.c1.l);          // a0 + a1        < 2p
+  fp_add_nr(d.l, a.c0.l, pp.l);            // a0 + p         < 2p
+  fp_sub_nr(d.l, d.l, a.c1.l);             // a0 + p - a1    in (0, 2p)
+  uint32_t t[16];
+  fp_mul_wide(t, a.c0.l, a.c1.l);
+  wide_dbl(t);
+  Fp2 r;
+  r.c0 = fp_mul(s, d);
+  r.c1 = fp_redc_wide(t);
+  return r;
+#else
   Fp t = fp_mul(a.c0, a.c1);
   Fp s = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
   return Fp2{s, fp_dbl(t)};
+#endif
 }
 
 // FieldExtension::scale by a base-field element (extensions.rs:86-94)

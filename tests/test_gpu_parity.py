@@ -347,3 +347,24 @@ def test_pairing_check_fixed_groth16_shape(eng):
     assert r.tolist() == [False]
     with pytest.raises(Exception):
         eng.pairing_check_fixed_batch(G1[:5], G2v[:1], co[:2], 3, 2)
+
+
+def test_validation(eng):
+    """G1Affine::new (g1.rs:111-132) and G2Projective::new (g2.rs:460-525) verdicts per point."""
+    from tests.test_hostsim import _twist_points_outside_subgroup
+
+    rng = random.Random(20)
+    g1 = [o.G1_GEN, w.rand_g1(rng), (5, 7, False), (o.P, 2, False), (0, 1, True)]
+    st = eng.g1_validate_batch(arr([w.fp_b(p[0] % (1 << 256)) + w.fp_b(p[1]) for p in g1]), g1_inf=[p[2] for p in g1])
+    assert st.tolist() == [0, 0, -3, -6, 0]
+    assert [o.g1_affine_new(p[0], p[1]) for p in g1[:3]] == ["ok", "ok", "NotOnCurve"]
+    good = [o.G2_GEN] + [w.rand_g2(rng) for _ in range(3)]
+    bad = _twist_points_outside_subgroup(rng, 3)
+    off = (good[1][0], o.fp2_add(good[1][1], o.FP2_ONE), False)
+    big = ((o.P + 1, good[2][0][1]), good[2][1], False)
+    pts = good + bad + [off, big, (o.FP2_ZERO, o.FP2_ONE, True)]
+    raw = arr([b"".join(w.fp_b(c) for c in (q[0][0], q[0][1], q[1][0], q[1][1])) for q in pts])
+    st = eng.g2_validate_batch(raw, g2_inf=[q[2] for q in pts])
+    assert st.tolist() == [0] * 4 + [-4] * 3 + [-3, -6, 0]
+    names = {"ok": 0, "NotOnCurve": -3, "NotInSubgroup": -4}
+    assert [names[o.g2_projective_new(q[0], q[1])] for q in good + bad + [off]] == st.tolist()[:8]

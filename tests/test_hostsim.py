@@ -165,3 +165,27 @@ def test_precompute_and_glued(hs):
             keep = [i for i in range(nv + nf) if not skip[i]]
             exp = o.glued_miller_loop([o.g2_precompute(qs[i]) for i in keep], [ps[i] for i in keep])
             assert w.b_fp12(f_out.raw) == exp, (nv, nf, skip)
+
+
+def _twist_points_outside_subgroup(rng, n):
+    out = []
+    while len(out) < n:
+        x = (rng.randrange(o.P), rng.randrange(o.P))
+        y = o.fp2_sqrt(o.fp2_add(o.fp2_mul(o.fp2_sqr(x), x), o.FP2_TWIST_CURVE_CONSTANT))
+        if y is not None:
+            out.append((x, y, False))
+    return out
+
+
+def test_g2_subgroup_check(hs):
+    """G2Projective::new subgroup relation (g2.rs:460-525)."""
+    rng = random.Random(7)
+    good = [o.G2_GEN, w.rand_g2(rng)]
+    bad = _twist_points_outside_subgroup(rng, 3)
+    for q in good + bad:
+        exp = o.g2_projective_new(q[0], q[1])
+        assert hs.hs_g2_on_curve(w.g2_b(q)) == 1
+        assert hs.hs_g2_in_subgroup(w.g2_b(q)) == (1 if exp == "ok" else 0)
+    assert [o.g2_projective_new(q[0], q[1]) for q in bad] == ["NotInSubgroup"] * 3
+    off = (good[1][0], o.fp2_add(good[1][1], o.FP2_ONE), False)
+    assert hs.hs_g2_on_curve(w.g2_b(off)) == 0 and o.g2_projective_new(off[0], off[1]) == "NotOnCurve"
