@@ -123,6 +123,28 @@ int sylow_b200_g1_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const u
 int sylow_b200_g2_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const uint8_t* g2_inf, size_t n,
                                  int8_t* status_out);
 
+/* ---- big-endian wire codecs ------------------------------------------------------------------------ */
+
+/* G1Affine::from_be_bytes (g1.rs:151-280) / G2Affine::from_be_bytes (g2.rs:361-433) over a batch: 64 / 128
+ * big-endian bytes per point (G2: imaginary parts first, g2.rs:325-328) -> wire form, infinity flags and a
+ * status per point (0, SYLOW_B200_ERR_DECODE, _NOT_ON_CURVE, _NOT_IN_SUBGROUP); invalid points decode to
+ * (0, 1).  eip_mode = 0: sylow's codec (bit 7 of byte 0 flags infinity, which must be x = 0, y = 1);
+ * eip_mode = 1: EIP-196/197 (all-zero = infinity, no flag bit; examples/reth_bn128.rs:118-126,187-194). */
+int sylow_b200_g1_from_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* be /* n*64 */, size_t n, int eip_mode,
+                                      uint8_t* g1_out, uint8_t* inf_out, int8_t* status_out);
+int sylow_b200_g2_from_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* be /* n*128 */, size_t n, int eip_mode,
+                                      uint8_t* g2_out, uint8_t* inf_out, int8_t* status_out);
+/* to_be_bytes / to_be_bytes_scrubbed (g1.rs:136-160, g2.rs:319-333). */
+int sylow_b200_g1_to_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, size_t n, int scrubbed,
+                                    uint8_t* be_out /* n*64 */);
+int sylow_b200_g2_to_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const uint8_t* g2_inf, size_t n, int scrubbed,
+                                    uint8_t* be_out /* n*128 */);
+/* The EIP-197 ecPairing precompile body (examples/reth_bn128.rs:156-217) for n_checks inputs of k pairs each
+ * (k * 192 big-endian bytes per input): decode, validate (field range, curve, G2 subgroup), glued_pairing ==
+ * identity.  ok_out[c] = 1/0; status_out[c] = 0 or the first decode/validation error of input c (then ok = 0). */
+int sylow_b200_eip197_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* input, size_t k, size_t n_checks,
+                                          uint8_t* ok_out, int8_t* status_out);
+
 /* ---- scalar multiplication --------------------------------------------------------------------- */
 
 /* out[i] = affine(scalars[i] * pts[i]);  replaces `&G1Projective * &Fp` + GroupAffine::from
@@ -131,6 +153,11 @@ int sylow_b200_g1_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, 
                             const uint8_t* scalars /* n*32 */, size_t n, uint8_t* out /* n*64 */, uint8_t* out_inf);
 int sylow_b200_g2_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts /* n*128 */, const uint8_t* pts_inf,
                             const uint8_t* scalars /* n*32 */, size_t n, uint8_t* out /* n*128 */, uint8_t* out_inf);
+
+/* out[i] = gt[i] * scalars[i] in sylow's additive notation, i.e. gt[i]^scalars[i] in Fp12  (`&Gt * &Fr`,
+ * groups/gt.rs:188-215).  gt[i] must be a Gt value (a final-exponentiation output: cyclotomic subgroup). */
+int sylow_b200_gt_mul_batch(sylow_b200_ctx* ctx, const uint8_t* gt /* n*384 */, const uint8_t* scalars /* n*32 */,
+                            size_t n, uint8_t* out /* n*384 */);
 
 /* ---- hash to curve / BLS ------------------------------------------------------------------------ */
 

@@ -924,3 +924,18 @@ def fp2_sqrt(a):
         b = fp2_pow(fp2_add(FP2_ONE, alpha), (P - 1) // 2)
         r = fp2_mul(b, x0)
     return r if fp2_sqr(r) == a else None
+
+
+def gt_mul(g, k: int):
+    """`&Gt * &Fr`: NAF square-and-multiply over 256 digits with double = Fp12 square and neg = conjugate,
+    src/groups/gt.rs:188-215 (double :268-270, neg :124-126)."""
+    np_, nm = fp_compute_naf(k)
+    res = FP12_ONE
+    neg = fp12_conj(g)
+    for i in reversed(range(256)):
+        res = fp12_sqr(res)
+        if (np_ >> i) & 1:
+            res = fp12_mul(res, g)
+        elif (nm >> i) & 1:
+            res = fp12_mul(res, neg)
+    return res

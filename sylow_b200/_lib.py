@@ -35,6 +35,12 @@ _SIGNATURES = {
     "sylow_b200_tables_to_device": (c_int, [_P, _P, c_size_t, _P, _P]),
     "sylow_b200_g1_validate_batch": (c_int, [_P, _P, _P, c_size_t, _P]),
     "sylow_b200_g2_validate_batch": (c_int, [_P, _P, _P, c_size_t, _P]),
+    "sylow_b200_g1_from_be_bytes_batch": (c_int, [_P, _P, c_size_t, c_int, _P, _P, _P]),
+    "sylow_b200_g2_from_be_bytes_batch": (c_int, [_P, _P, c_size_t, c_int, _P, _P, _P]),
+    "sylow_b200_g1_to_be_bytes_batch": (c_int, [_P, _P, _P, c_size_t, c_int, _P]),
+    "sylow_b200_g2_to_be_bytes_batch": (c_int, [_P, _P, _P, c_size_t, c_int, _P]),
+    "sylow_b200_eip197_pairing_check_batch": (c_int, [_P, _P, c_size_t, c_size_t, _P, _P]),
+    "sylow_b200_gt_mul_batch": (c_int, [_P, _P, _P, c_size_t, _P]),
     "sylow_b200_g1_mul_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_g2_mul_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_hash_to_g1_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P]),

@@ -195,6 +195,51 @@ class Engine:
         self._ck(self._lib.sylow_b200_g2_validate_batch(self._h, _ptr(g2), _ptr(g2_inf), n, _ptr(st)), "g2_validate_batch")
         return st
 
+    # ------------------------------------------------------------------ big-endian codecs
+    def _from_be(self, fn, width, be, eip_mode):
+        be = _u8(be, width, "be")
+        n = be.shape[0]
+        out = np.empty((n, width), dtype=np.uint8)
+        inf = np.empty(n, dtype=np.uint8)
+        st = np.empty(n, dtype=np.int8)
+        self._ck(fn(self._h, _ptr(be), n, int(bool(eip_mode)), _ptr(out), _ptr(inf), _ptr(st)), fn.__name__)
+        return out, inf, st
+
+    def g1_from_be_bytes_batch(self, be, eip_mode=False):
+        return self._from_be(self._lib.sylow_b200_g1_from_be_bytes_batch, 64, be, eip_mode)
+
+    def g2_from_be_bytes_batch(self, be, eip_mode=False):
+        return self._from_be(self._lib.sylow_b200_g2_from_be_bytes_batch, 128, be, eip_mode)
+
+    def _to_be(self, fn, width, pts, inf, scrubbed):
+        pts = _u8(pts, width, "pts")
+        n = pts.shape[0]
+        inf = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8).reshape(n)
+        out = np.empty((n, width), dtype=np.uint8)
+        self._ck(fn(self._h, _ptr(pts), _ptr(inf), n, int(bool(scrubbed)), _ptr(out)), fn.__name__)
+        return out
+
+    def g1_to_be_bytes_batch(self, g1, g1_inf=None, scrubbed=False):
+        return self._to_be(self._lib.sylow_b200_g1_to_be_bytes_batch, 64, g1, g1_inf, scrubbed)
+
+    def g2_to_be_bytes_batch(self, g2, g2_inf=None, scrubbed=False):
+        return self._to_be(self._lib.sylow_b200_g2_to_be_bytes_batch, 128, g2, g2_inf, scrubbed)
+
+    def eip197_pairing_check_batch(self, inputs, pairs_per_check: int):
+        """inputs: (n_checks, k*192) big-endian calldata; returns (ok bool array, int8 status array)."""
+        k = int(pairs_per_check)
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        if inputs.ndim == 1:
+            inputs = inputs.reshape(1, -1)
+        if inputs.shape[1] != k * 192:
+            raise ValueError("each input must be k*192 bytes")
+        n = inputs.shape[0]
+        ok = np.empty(n, dtype=np.uint8)
+        st = np.empty(n, dtype=np.int8)
+        self._ck(self._lib.sylow_b200_eip197_pairing_check_batch(self._h, _ptr(inputs), k, n, _ptr(ok), _ptr(st)),
+                 "eip197_pairing_check_batch")
+        return ok.astype(bool), st
+
     # ------------------------------------------------------------------ scalar multiplication
     def _mul(self, fn, width, pts, scalars, pts_inf):
         pts = _u8(pts, width, "pts")
@@ -213,6 +258,16 @@ class Engine:
 
     def g2_mul_batch(self, pts, scalars, pts_inf=None):
         return self._mul(self._lib.sylow_b200_g2_mul_batch, 128, pts, scalars, pts_inf)
+
+    def gt_mul_batch(self, gt, scalars) -> np.ndarray:
+        """`Gt * Fr`: gt[i]^scalars[i] (gt must be final-exponentiation outputs)."""
+        gt = _u8(gt, 384, "gt")
+        scalars = _u8(scalars, 32, "scalars")
+        if gt.shape[0] != scalars.shape[0]:
+            raise ValueError("gt and scalars batch sizes differ")
+        out = np.empty_like(gt)
+        self._ck(self._lib.sylow_b200_gt_mul_batch(self._h, _ptr(gt), _ptr(scalars), gt.shape[0], _ptr(out)), "gt_mul_batch")
+        return out
 
     # ------------------------------------------------------------------ hash / BLS
     @staticmethod

@@ -267,4 +267,27 @@ SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
   return fp12_mul(u, r);
 }
 
+
+// `&Gt * &Fr` (gt.rs:188-215): g^k for g in the cyclotomic subgroup (every Gt value is a final
+// exponentiation output).  The reference runs a 256-digit NAF ladder with Fp12 squarings; the value g^k does
+// not depend on the chain, so this uses fixed 4-bit windows with cyclotomic squarings and no data-dependent
+// control flow.
+SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
+  Fp12 tab[16];
+  tab[0] = fp12_one();
+  tab[1] = g;
+  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? fp12_mul(tab[i - 1], g) : cyclotomic_squared(tab[i >> 1]);
+  Fp12 acc = tab[k[7] >> 28];
+  for (int w = 62; w >= 0; w--) {
+    SY_LOOP_SYNC();
+    acc = cyclotomic_squared(acc);
+    acc = cyclotomic_squared(acc);
+    acc = cyclotomic_squared(acc);
+    acc = cyclotomic_squared(acc);
+    uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+    acc = fp12_mul(acc, tab[d]);
+  }
+  return acc;
+}
+
 }  // namespace sylow

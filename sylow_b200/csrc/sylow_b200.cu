@@ -235,12 +235,12 @@ k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offs
 
 // status[i]: 0 ok, SYLOW_B200_ERR_DECODE (a coordinate >= p), SYLOW_B200_ERR_NOT_ON_CURVE   (g1.rs:111-132)
 __global__ void k_g1_validate(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ inf, size_t n,
-                              int8_t* __restrict__ status) {
+                              int8_t* __restrict__ status, int keep_errors) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp xr = fp_load_raw(g1 + i * 64), yr = fp_load_raw(g1 + i * 64 + 32);
-  int8_t st = 0;
-  if (!(inf && inf[i])) {
+  int8_t st = keep_errors ? status[i] : 0;
+  if (st == 0 && !(inf && inf[i])) {
     if (!fp_raw_is_canonical(xr) || !fp_raw_is_canonical(yr))
       st = SYLOW_B200_ERR_DECODE;
     else if (!g1_on_curve(fp_to_mont(xr), fp_to_mont(yr)))
@@ -251,7 +251,8 @@ __global__ void k_g1_validate(const uint8_t* __restrict__ g1, const uint8_t* __r
 
 // + SYLOW_B200_ERR_NOT_IN_SUBGROUP: (x+1)Q + psi(xQ) + psi^2(xQ) != psi^3(2xQ)   (g2.rs:279-297, :460-525)
 __global__ void __launch_bounds__(SY_MUL_THREADS, 1)
-k_g2_validate(const uint8_t* __restrict__ g2, const uint8_t* __restrict__ inf, size_t n, int8_t* __restrict__ status) {
+k_g2_validate(const uint8_t* __restrict__ g2, const uint8_t* __restrict__ inf, size_t n, int8_t* __restrict__ status,
+              int keep_errors) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
   Fp2 xr = fp2_load_raw(g2 + i * 128), yr = fp2_load_raw(g2 + i * 128 + 64);
@@ -261,8 +262,8 @@ k_g2_validate(const uint8_t* __restrict__ g2, const uint8_t* __restrict__ inf, s
   bool on = g2_on_curve(x, y);
   bool sub = g2_in_subgroup(x, y);  // every thread runs the (block-synchronised) ladder
   if (i0 >= n) return;
-  int8_t st = 0;
-  if (!(inf && inf[i])) {
+  int8_t st = keep_errors ? status[i] : 0;
+  if (st == 0 && !(inf && inf[i])) {
     if (!canon)
       st = SYLOW_B200_ERR_DECODE;
     else if (!on)
@@ -271,6 +272,140 @@ k_g2_validate(const uint8_t* __restrict__ g2, const uint8_t* __restrict__ inf, s
       st = SYLOW_B200_ERR_NOT_IN_SUBGROUP;
   }
   status[i] = st;
+}
+
+
+// ---- big-endian codecs -------------------------------------------------------------
+// 32 big-endian bytes -> Fp limbs (little-endian words), no reduction
+__device__ __forceinline__ Fp fp_from_be32(const uint8_t* b, uint32_t top_mask) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint8_t* q = b + 28 - 4 * i;
+    r.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+  }
+  r.l[7] &= top_mask;
+  return r;
+}
+__device__ __forceinline__ void fp_to_be32(uint8_t* b, const Fp& v) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint8_t* q = b + 28 - 4 * i;
+    q[0] = (uint8_t)(v.l[i] >> 24);
+    q[1] = (uint8_t)(v.l[i] >> 16);
+    q[2] = (uint8_t)(v.l[i] >> 8);
+    q[3] = (uint8_t)v.l[i];
+  }
+}
+__device__ __forceinline__ bool fp_raw_is_u32(const Fp& a, uint32_t v) {
+  uint32_t o = a.l[0] ^ v;
+#pragma unroll
+  for (int i = 1; i < 8; i++) o |= a.l[i];
+  return o == 0;
+}
+// NF big-endian field elements per point (2 for G1, 4 for G2 with the imaginary parts first,
+// g2.rs:325-328) -> little-endian wire form + infinity flag + decode status.
+//   mode 0: sylow's codec (g1.rs:151-280, g2.rs:319-433): bit 7 of byte 0 flags infinity and must come
+//           with x = 0, y = 1;   mode 1: EIP-196/197: the all-zero encoding is the point at infinity
+//           (examples/reth_bn128.rs:118-126,187-194) and there is no flag bit.
+template <int NF>
+__global__ void k_decode_be(const uint8_t* __restrict__ be, size_t stride, size_t n, int mode, uint8_t* __restrict__ out,
+                            uint8_t* __restrict__ out_inf, int8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* b = be + i * stride;
+  bool flag = mode == 0 && (b[0] >> 7);
+  Fp f[NF];
+  bool canon = true, all_zero = true;
+  for (int j = 0; j < NF; j++) {
+    f[j] = fp_from_be32(b + 32 * j, (mode == 0 && j == 0) ? 0x7fffffffu : 0xffffffffu);
+    canon &= fp_raw_is_canonical(f[j]);
+    all_zero &= fp_raw_is_u32(f[j], 0);
+  }
+  // wire order: G1 (x, y); G2 (x.c0, x.c1, y.c0, y.c1) from (x.c1, x.c0, y.c1, y.c0)
+  Fp w[NF];
+  if (NF == 2) {
+    w[0] = f[0];
+    w[1] = f[1];
+  } else {
+    w[0] = f[1];
+    w[1] = f[0];
+    w[2] = f[3];
+    w[3] = f[2];
+  }
+  bool x_zero = true, y_one = true;
+  for (int j = 0; j < NF / 2; j++) x_zero &= fp_raw_is_u32(w[j], 0);
+  for (int j = 0; j < NF / 2; j++) y_one &= fp_raw_is_u32(w[NF / 2 + j], j == 0 ? 1u : 0u);
+  int8_t st = canon ? 0 : SYLOW_B200_ERR_DECODE;
+  bool inf = false;
+  if (mode == 0) {
+    if (flag) {
+      inf = true;
+      if (st == 0 && !(x_zero && y_one)) st = SYLOW_B200_ERR_DECODE;
+    }
+  } else {
+    inf = all_zero;
+  }
+  if (inf || st != 0) {  // GroupAffine::zero(): (0, 1, infinity)
+    for (int j = 0; j < NF; j++) w[j] = fp_zero();
+    w[NF / 2].l[0] = 1;
+  }
+  for (int j = 0; j < NF; j++) fp_store_raw(out + i * (32 * NF) + 32 * j, w[j]);
+  out_inf[i] = inf ? 1 : 0;
+  status[i] = st;
+}
+
+// wire form -> big-endian (to_be_bytes / to_be_bytes_scrubbed, g1.rs:136-160, g2.rs:319-333)
+template <int NF>
+__global__ void k_encode_be(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ inf, size_t n, int scrub,
+                            uint8_t* __restrict__ be) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool is_inf = inf && inf[i];
+  Fp w[NF];
+  for (int j = 0; j < NF; j++) w[j] = fp_load_raw(pts + i * (32 * NF) + 32 * j);
+  if (is_inf) {
+    for (int j = 0; j < NF; j++) w[j] = fp_zero();
+    if (!scrub) w[NF / 2].l[0] = 1;
+  }
+  uint8_t* b = be + i * (32 * NF);
+  if (NF == 2) {
+    fp_to_be32(b, w[0]);
+    fp_to_be32(b + 32, w[1]);
+  } else {
+    fp_to_be32(b, w[1]);
+    fp_to_be32(b + 32, w[0]);
+    fp_to_be32(b + 64, w[3]);
+    fp_to_be32(b + 96, w[2]);
+  }
+  if (is_inf && !scrub) b[0] |= 0x80;
+}
+
+// per check: the first non-zero pair status wins and forces ok = 0
+__global__ void k_fold_status(const int8_t* __restrict__ st_g1, const int8_t* __restrict__ st_g2, size_t k, size_t n_checks,
+                              uint8_t* __restrict__ ok, int8_t* __restrict__ status) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_checks) return;
+  int8_t st = 0;
+  for (size_t j = 0; j < k && st == 0; j++) {
+    st = st_g1[c * k + j];
+    if (st == 0) st = st_g2[c * k + j];
+  }
+  if (st != 0) ok[c] = 0;
+  status[c] = st;
+}
+
+
+// out[i] = gt[i]^scalars[i]   (`Gt * Fr`, gt.rs:188-215)
+__global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
+k_gt_pow(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
+  Fp12 g = fp12_load(gt + i * 384);
+  Fp k = fp_load_raw(scalars + i * 32);
+  Fp12 r = gt_pow(g, k.l);
+  if (i0 >= n) return;
+  fp12_store(out + i * 384, r);
 }
 
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
@@ -1088,7 +1223,7 @@ int sylow_b200_g1_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const u
   CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
   CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
   CKS(reserve(ctx, ctx->out, n));
-  k_g1_validate<<<nblocks(n, 128), 128, 0, ctx->stream>>>(d1, d1i, n, reinterpret_cast<int8_t*>(ctx->out.p));
+  k_g1_validate<<<nblocks(n, 128), 128, 0, ctx->stream>>>(d1, d1i, n, reinterpret_cast<int8_t*>(ctx->out.p), 0);
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(status_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
@@ -1104,9 +1239,130 @@ int sylow_b200_g2_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const u
   CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
   CKS(reserve(ctx, ctx->out, n));
   k_g2_validate<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, ctx->stream>>>(d2, d2i, n,
-                                                                               reinterpret_cast<int8_t*>(ctx->out.p));
+                                                                               reinterpret_cast<int8_t*>(ctx->out.p), 0);
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(status_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------- big-endian codecs
+static int from_be(sylow_b200_ctx* ctx, int g2, const uint8_t* be, size_t n, int mode, int validate, uint8_t* out,
+                   uint8_t* inf_out, int8_t* status_out) {
+  ENTER(ctx);
+  if (n && (!be || !out || !inf_out || !status_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  size_t w = g2 ? 128 : 64;
+  const uint8_t* dbe;
+  CKS(to_dev(ctx, ctx->in_c, be, n * w, &dbe));
+  CKS(reserve(ctx, ctx->in_a, n * w));
+  CKS(reserve(ctx, ctx->flag_a, n));
+  CKS(reserve(ctx, ctx->out, n));
+  int8_t* st = reinterpret_cast<int8_t*>(ctx->out.p);
+  if (g2) {
+    k_decode_be<4><<<nblocks(n, 128), 128, 0, ctx->stream>>>(dbe, 128, n, mode, ctx->in_a.p, ctx->flag_a.p, st);
+    LAUNCHED(ctx);
+    if (validate) {
+      k_g2_validate<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, ctx->stream>>>(ctx->in_a.p, ctx->flag_a.p, n, st, 1);
+      LAUNCHED(ctx);
+    }
+  } else {
+    k_decode_be<2><<<nblocks(n, 128), 128, 0, ctx->stream>>>(dbe, 64, n, mode, ctx->in_a.p, ctx->flag_a.p, st);
+    LAUNCHED(ctx);
+    if (validate) {
+      k_g1_validate<<<nblocks(n, 128), 128, 0, ctx->stream>>>(ctx->in_a.p, ctx->flag_a.p, n, st, 1);
+      LAUNCHED(ctx);
+    }
+  }
+  CK(cudaMemcpyAsync(out, ctx->in_a.p, n * w, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(inf_out, ctx->flag_a.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(status_out, st, n, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+int sylow_b200_g1_from_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* be, size_t n, int eip_mode, uint8_t* g1_out,
+                                      uint8_t* inf_out, int8_t* status_out) {
+  return from_be(ctx, 0, be, n, eip_mode ? 1 : 0, 1, g1_out, inf_out, status_out);
+}
+int sylow_b200_g2_from_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* be, size_t n, int eip_mode, uint8_t* g2_out,
+                                      uint8_t* inf_out, int8_t* status_out) {
+  return from_be(ctx, 1, be, n, eip_mode ? 1 : 0, 1, g2_out, inf_out, status_out);
+}
+static int to_be(sylow_b200_ctx* ctx, int g2, const uint8_t* pts, const uint8_t* inf, size_t n, int scrub, uint8_t* be_out) {
+  ENTER(ctx);
+  if (n && (!pts || !be_out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  size_t w = g2 ? 128 : 64;
+  const uint8_t *dp, *di;
+  CKS(to_dev(ctx, ctx->in_a, pts, n * w, &dp));
+  CKS(to_dev(ctx, ctx->flag_a, inf, n, &di));
+  CKS(reserve(ctx, ctx->out, n * w));
+  if (g2)
+    k_encode_be<4><<<nblocks(n, 128), 128, 0, ctx->stream>>>(dp, di, n, scrub, ctx->out.p);
+  else
+    k_encode_be<2><<<nblocks(n, 128), 128, 0, ctx->stream>>>(dp, di, n, scrub, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(be_out, ctx->out.p, n * w, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+int sylow_b200_g1_to_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, size_t n, int scrubbed,
+                                    uint8_t* be_out) {
+  return to_be(ctx, 0, g1, g1_inf, n, scrubbed, be_out);
+}
+int sylow_b200_g2_to_be_bytes_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const uint8_t* g2_inf, size_t n, int scrubbed,
+                                    uint8_t* be_out) {
+  return to_be(ctx, 1, g2, g2_inf, n, scrubbed, be_out);
+}
+
+int sylow_b200_eip197_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* input, size_t k, size_t n_checks,
+                                          uint8_t* ok_out, int8_t* status_out) {
+  ENTER(ctx);
+  if (n_checks && (!ok_out || !status_out || (k && !input))) return SYLOW_B200_ERR_ARG;
+  if (!n_checks) return 0;
+  size_t n = k * n_checks;
+  CKS(reserve(ctx, ctx->out, 2 * n_checks + 64));
+  uint8_t* d_ok = ctx->out.p;
+  int8_t* d_st = reinterpret_cast<int8_t*>(ctx->out.p + ((n_checks + 15) / 16) * 16);
+  if (n) {
+    const uint8_t* din;
+    CKS(to_dev(ctx, ctx->in_c, input, n * 192, &din));
+    CKS(reserve(ctx, ctx->in_a, n * 64));
+    CKS(reserve(ctx, ctx->in_b, n * 128));
+    CKS(reserve(ctx, ctx->flag_a, n));
+    CKS(reserve(ctx, ctx->flag_b, n));
+    CKS(reserve(ctx, ctx->scratch2, 2 * n + 64));
+    int8_t* st1 = reinterpret_cast<int8_t*>(ctx->scratch2.p);
+    int8_t* st2 = st1 + n;
+    k_decode_be<2><<<nblocks(n, 128), 128, 0, ctx->stream>>>(din, 192, n, 1, ctx->in_a.p, ctx->flag_a.p, st1);
+    LAUNCHED(ctx);
+    k_decode_be<4><<<nblocks(n, 128), 128, 0, ctx->stream>>>(din + 64, 192, n, 1, ctx->in_b.p, ctx->flag_b.p, st2);
+    LAUNCHED(ctx);
+    k_g1_validate<<<nblocks(n, 128), 128, 0, ctx->stream>>>(ctx->in_a.p, ctx->flag_a.p, n, st1, 1);
+    LAUNCHED(ctx);
+    k_g2_validate<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, ctx->stream>>>(ctx->in_b.p, ctx->flag_b.p, n, st2, 1);
+    LAUNCHED(ctx);
+    CKS(sylow_b200_pairing_check_batch_dev(ctx, ctx->in_a.p, ctx->flag_a.p, ctx->in_b.p, ctx->flag_b.p, k, n_checks, d_ok,
+                                           nullptr));
+    k_fold_status<<<nblocks(n_checks, 128), 128, 0, ctx->stream>>>(st1, st2, k, n_checks, d_ok, d_st);
+    LAUNCHED(ctx);
+  } else {
+    CK(cudaMemsetAsync(d_ok, 1, n_checks, ctx->stream));  // empty input: success (reth_bn128.rs:173-175)
+    CK(cudaMemsetAsync(d_st, 0, n_checks, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(ok_out, d_ok, n_checks, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(status_out, d_st, n_checks, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_gt_mul_batch(sylow_b200_ctx* ctx, const uint8_t* gt, const uint8_t* scalars, size_t n, uint8_t* out) {
+  ENTER(ctx);
+  if (n && (!gt || !scalars || !out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  const uint8_t *dg, *dk;
+  CKS(to_dev(ctx, ctx->in_a, gt, n * 384, &dg));
+  CKS(to_dev(ctx, ctx->in_b, scalars, n * 32, &dk));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  k_gt_pow<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(dg, dk, n, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
 }
 

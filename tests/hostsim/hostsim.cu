@@ -105,6 +105,11 @@ int hs_g1_add(const uint8_t* p, int pinf, const uint8_t* q, int qinf, uint8_t* o
 int hs_g2_in_subgroup(const uint8_t* g2) { return g2_in_subgroup(fp2_load(g2), fp2_load(g2 + 64)) ? 1 : 0; }
 int hs_g2_on_curve(const uint8_t* g2) { return g2_on_curve(fp2_load(g2), fp2_load(g2 + 64)) ? 1 : 0; }
 
+void hs_gt_pow(const uint8_t* g, const uint8_t* k, uint8_t* out) {
+  Fp kk = fp_load_raw(k);
+  fp12_store(out, gt_pow(fp12_load(g), kk.l));
+}
+
 void hs_keccak256(const uint8_t* msg, size_t n, uint8_t* out32) {
   Keccak256 k;
   keccak_init(k);

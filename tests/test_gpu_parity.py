@@ -368,3 +368,86 @@ def test_validation(eng):
     assert st.tolist() == [0] * 4 + [-4] * 3 + [-3, -6, 0]
     names = {"ok": 0, "NotOnCurve": -3, "NotInSubgroup": -4}
     assert [names[o.g2_projective_new(q[0], q[1])] for q in good + bad + [off]] == st.tolist()[:8]
+
+
+def _g1_be(p):
+    b = bytearray((0 if p[2] else p[0]).to_bytes(32, "big") + (1 if p[2] else p[1]).to_bytes(32, "big"))
+    if p[2]:
+        b[0] |= 0x80
+    return bytes(b)
+
+
+def _g2_be(q):
+    x, y = (o.FP2_ZERO, o.FP2_ONE) if q[2] else (q[0], q[1])
+    b = bytearray(b"".join(c.to_bytes(32, "big") for c in (x[1], x[0], y[1], y[0])))
+    if q[2]:
+        b[0] |= 0x80
+    return bytes(b)
+
+
+def test_be_codecs(eng):
+    """to_be_bytes / from_be_bytes (g1.rs:136-280, g2.rs:319-433; byte tests at src/groups/mod.rs:769-873)."""
+    rng = random.Random(23)
+    g1 = [o.G1_GEN, w.rand_g1(rng), (0, 1, True)]
+    enc = eng.g1_to_be_bytes_batch(arr([w.g1_b(p) for p in g1]), [p[2] for p in g1])
+    assert [bytes(r) for r in enc] == [_g1_be(p) for p in g1]
+    assert bytes(eng.g1_to_be_bytes_batch(arr([w.g1_b(g1[2])]), [1], scrubbed=True)[0]) == bytes(64)
+    bad_curve = (1).to_bytes(32, "big") + (3).to_bytes(32, "big")
+    over = (o.P + 1).to_bytes(32, "big") + (2).to_bytes(32, "big")
+    bad_inf = bytearray(_g1_be(g1[1]))
+    bad_inf[0] |= 0x80  # infinity flag on a finite point: rejected (g1.rs:274-276)
+    out, inf, st = eng.g1_from_be_bytes_batch(arr([bytes(r) for r in enc] + [bad_curve, over, bytes(bad_inf)]))
+    assert st.tolist() == [0, 0, 0, -3, -6, -6] and inf.tolist()[:3] == [0, 0, 1]
+    assert [w.b_g1(bytes(r), i) for r, i in zip(out[:3], inf[:3])] == g1
+    g2 = [o.G2_GEN, w.rand_g2(rng), (o.FP2_ZERO, o.FP2_ONE, True)]
+    enc2 = eng.g2_to_be_bytes_batch(arr([w.g2_b(q) for q in g2]), [q[2] for q in g2])
+    assert [bytes(r) for r in enc2] == [_g2_be(q) for q in g2]
+    out, inf, st = eng.g2_from_be_bytes_batch(enc2)
+    assert st.tolist() == [0, 0, 0] and [w.b_g2(bytes(r), i) for r, i in zip(out, inf)] == g2
+    # EIP mode: all-zero is infinity, the MSB is part of the value (so a flagged encoding is out of range)
+    out, inf, st = eng.g1_from_be_bytes_batch(arr([bytes(64), _g1_be(g1[2])]), eip_mode=True)
+    assert inf.tolist() == [1, 0] and st.tolist() == [0, -6]
+
+
+def test_eip197_precompile(eng, kats):
+    """ecPairing body (examples/reth_bn128.rs:156-217) on the reference's vector and on broken inputs."""
+    from tests.test_hostsim import _twist_points_outside_subgroup
+
+    good = bytes.fromhex(kats["eip197_pair"]["input"])
+    rng = random.Random(24)
+    wrong = bytearray(good)
+    wrong[0:64] = _g1_be(w.rand_g1(rng))  # valid points, product != 1
+    off_curve = bytearray(good)
+    off_curve[63] ^= 1
+    over = bytearray(good)
+    over[0:32] = (o.P + 5).to_bytes(32, "big")
+    q = _twist_points_outside_subgroup(rng, 1)[0]
+    not_sub = bytearray(good)
+    not_sub[64:192] = _g2_be(q)
+    with_inf = bytearray(good)
+    with_inf[192:256] = bytes(64)  # G1 of pair 2 = infinity -> that pair contributes 1 -> product != 1
+    both_inf = bytes(384)  # all pairs infinite: product of ones
+    ok, st = eng.eip197_pairing_check_batch(arr([good, bytes(wrong), bytes(off_curve), bytes(over), bytes(not_sub),
+                                                 bytes(with_inf), both_inf]), 2)
+    assert ok.tolist() == [True, False, False, False, False, False, True]
+    assert st.tolist() == [0, 0, -3, -6, -4, 0, 0]
+    assert bytes.fromhex(kats["eip197_pair"]["expected"])[-1] == 1
+
+
+def test_gt_mul_bilinearity(eng):
+    """src/pairing.rs:1192-1213: pairing(p, q) * s == pairing(s p, q) == pairing(p, s q); `Gt * Fr` gt.rs:188-215."""
+    rng = random.Random(25)
+    n = 5
+    ps = [w.rand_g1(rng) for _ in range(n)]
+    qs = [w.rand_g2(rng) for _ in range(n)]
+    ss = [rng.randrange(1, o.R_ORDER) for _ in range(n - 2)] + [0, o.R_ORDER - 1]
+    G1, G2, S = arr([w.g1_b(p) for p in ps]), arr([w.g2_b(q) for q in qs]), arr([w.fp_b(s) for s in ss])
+    a = eng.gt_mul_batch(eng.pairing_batch(G1, G2), S)
+    sP, sPinf = eng.g1_mul_batch(G1, S)
+    b = eng.pairing_batch(sP, G2, g1_inf=sPinf)
+    assert (a == b).all()
+    gt0 = o.pairing_affine(ps[0], qs[0])
+    assert w.b_fp12(bytes(a[0])) == o.gt_mul(gt0, ss[0])
+    # -1 * a + a == identity (additive notation)
+    assert w.b_fp12(bytes(a[n - 1])) == o.fp12_conj(o.pairing_affine(ps[n - 1], qs[n - 1]))
+    assert w.b_fp12(bytes(a[n - 2])) == o.FP12_ONE

@@ -189,3 +189,13 @@ def test_g2_subgroup_check(hs):
     assert [o.g2_projective_new(q[0], q[1]) for q in bad] == ["NotInSubgroup"] * 3
     off = (good[1][0], o.fp2_add(good[1][1], o.FP2_ONE), False)
     assert hs.hs_g2_on_curve(w.g2_b(off)) == 0 and o.g2_projective_new(off[0], off[1]) == "NotOnCurve"
+
+
+def test_gt_pow(hs):
+    """`Gt * Fr` (gt.rs:188-215) and the bilinearity identity e(P,Q)*s == e(sP,Q) (pairing.rs:1192-1213)."""
+    rng = random.Random(8)
+    g = o.pairing_affine(o.G1_GEN, o.G2_GEN)
+    out = ctypes.create_string_buffer(384)
+    for k in (0, 1, 2, o.R_ORDER - 1, rng.randrange(o.R_ORDER)):
+        hs.hs_gt_pow(w.fp12_b(g), w.fp_b(k), out)
+        assert w.b_fp12(out.raw) == o.gt_mul(g, k)
