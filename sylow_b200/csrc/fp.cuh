@@ -314,8 +314,10 @@ __device__ __forceinline__ void mont_round(uint32_t* X, uint32_t* Y, const uint3
       : "r"(m));
 }
 
-// r = a * b / R mod p, fully reduced.  Requires a * b < p * R (true for a, b < p and for the
-// to-Montgomery use a < 2^256, b = R^2 mod p).
+// r = a * b / R mod p, fully reduced.  Requires a < 2p (a is the multiplicand of every round: the
+// running value stays below a + p, which must fit the 8-limb accumulators) and a * b < p * R; b may be
+// ANY 256-bit value as long as the product bound holds - so conversions of unreduced inputs put the
+// constant first: fp_mul(R^2, x) is valid for every x < 2^256.
 __device__ __forceinline__ Fp fp_mul(const Fp& a, const Fp& b) {
   uint32_t ev[8], od[8];
   mont_round<true>(ev, od, a.l, b.l[0]);
@@ -695,7 +697,7 @@ inline void fp_add_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 
 SY_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 
-SY_HD Fp fp_to_mont(const Fp& a) { return fp_mul(a, fp_R2()); }
+SY_HD Fp fp_to_mont(const Fp& a) { return fp_mul(fp_R2(), a); }  // any a < 2^256 (reduces mod p)
 SY_HD Fp fp_from_mont(const Fp& a) {
   Fp one = fp_zero();
   one.l[0] = 1;

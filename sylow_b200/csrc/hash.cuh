@@ -106,8 +106,9 @@ SY_HD Fp fp_from_be48_mod(const uint8_t* b) {
     const uint8_t* q = b + 44 - 4 * i;
     lo.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
   }
-  // lo * R + hi * 2^256 * R  (mod p)
-  return fp_add(fp_mul(lo, fp_R2()), fp_mul(hi, fp_R3()));
+  // lo * R + hi * 2^256 * R  (mod p).  lo is an arbitrary 256-bit value (>= p four times out of five), so the
+  // constants go first: fp_mul's multiplicand must be < 2p, its multiplier may be any 256-bit value.
+  return fp_add(fp_mul(fp_R2(), lo), fp_mul(fp_R3(), hi));
 }
 
 // expand_message_xmd(msg, DST, 96) with Keccak-256, then two field elements.

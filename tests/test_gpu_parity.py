@@ -222,6 +222,29 @@ def test_hash_to_g1(eng):
                                                 for m in MSGS[:3]]
 
 
+def test_hash_to_g1_many(eng):
+    """Regression: hash_to_field feeds UNREDUCED 256-bit values into the Montgomery conversion; 4096 messages
+    against the C oracle (which is pinned to the Python oracle on the CPU tier)."""
+    from oracle import c_oracle as c
+
+    rs = np.random.RandomState(31)
+    n = 4096
+    lens = rs.randint(0, 80, size=n)
+    msgs = [bytes(rs.randint(0, 256, size=int(k), dtype=np.uint8)) for k in lens]
+    out, inf = eng.hash_to_g1_batch(msgs)
+    ref, rinf = c.hash_to_g1_batch(msgs)
+    assert (out == ref).all() and not inf.any() and not rinf.any()
+
+
+def test_unreduced_inputs_are_reduced_on_load(eng):
+    """Wire values >= p are reduced mod p by the loader (fp_mul(R^2, x) is valid for any 256-bit x)."""
+    vals = [o.P, o.P + 1, 2 * o.P + 5, (1 << 256) - 1, (1 << 255) + 12345, 5 * o.P + 7]
+    A = arr([w.fp_b(v) for v in vals])
+    Z = arr([w.fp_b(0)] * len(vals))
+    assert ints(eng.fp_op_batch(1, A, Z)) == [v % o.P for v in vals]
+    assert ints(eng.fp_op_batch(0, A, A)) == [v * v % o.P for v in vals]
+
+
 def test_sign_verify(eng):
     rng = random.Random(17)
     n = len(MSGS)
