@@ -37,8 +37,28 @@
 #ifndef SY_BLOCK_SYNC
 #define SY_BLOCK_SYNC 1
 #endif
+// SY_STAGGER (cycles): after each re-convergence the warps that share a scheduler with a lower-numbered warp
+// (warp id / 4 = 1, 2, ...) wait g * SY_STAGGER cycles.  Warps in lockstep are in the same phase of the code
+// (all in a multiplication or all in a carry chain) and queue on ONE pipe; a small skew lets one warp's
+// IMAD phase overlap the other's ALU phase while both stay inside the same instruction-cache window.
+#ifndef SY_STAGGER
+#define SY_STAGGER 0
+#endif
 #if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
+#if SY_STAGGER > 0
+__device__ __forceinline__ void sy_stagger() {
+  unsigned g = threadIdx.x >> 7;  // warp id / 4: position of this warp on its scheduler
+  if (g) {
+    long long t0 = clock64();
+    long long d = (long long)g * SY_STAGGER;
+    while (clock64() - t0 < d) {
+    }
+  }
+}
+#define SY_LOOP_SYNC() (__syncthreads(), sy_stagger())
+#else
 #define SY_LOOP_SYNC() __syncthreads()
+#endif
 #else
 #define SY_LOOP_SYNC() ((void)0)
 #endif
