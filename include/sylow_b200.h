@@ -239,7 +239,8 @@ int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, cons
  * runs `iters` loop iterations.  variant 0/1/2: 1/2/4 interleaved dependent Montgomery multiplications
  * per iteration (*ops_out = Fp multiplications; x136 = limb products).  variant 10: independent
  * mad.wide.u32; 11: independent 32-bit mad.lo.u32; 12: mad.lo.cc/madc.hi.cc carry chains (the
- * IMAD.WIDE.U32.X form fp_mul uses) - *ops_out = multiply-add instructions issued per thread x threads.
+ * IMAD.WIDE.U32.X form fp_mul uses); 13: independent fma.rn.f64 (the FP64 pipe, for comparison) - *ops_out =
+ * multiply-add instructions issued per thread x threads.
  * *ms_out = device time of the second of two launches. */
 int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms_out,
                           double* ops_out);

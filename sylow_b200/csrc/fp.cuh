@@ -70,7 +70,9 @@ __device__ __forceinline__ void sy_stagger() {
 
 namespace sylow {
 
-struct Fp {
+// 16-byte alignment lets every load/store of a field element (including the local-memory frame traffic of
+// the out-of-line Fp2 routines) be a 128-bit access.
+struct alignas(16) Fp {
   uint32_t l[8];
 };
 

@@ -510,6 +510,26 @@ __global__ void k_pipe_probe(int iters, const uint32_t* src, uint32_t* sink) {
   if (acc == 0x12345678u) sink[0] = acc;
 }
 
+// FP64 FMA probe (16 independent chains, 64 DFMA per loop iteration): how fast the OTHER multiplier on the SM
+// is.  Recorded for DESIGN.md section 7 (double-precision limb products as a possible second pipe).
+__global__ void k_dfma_probe(int iters, const uint32_t* src, uint32_t* sink) {
+  double a = 1.0 + (double)(src[0] & 1023) * 1e-9, b = 1e-7 + (double)(src[1] & 1023) * 1e-12;
+  double r[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) r[i] = (double)(threadIdx.x + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+      for (int c = 0; c < 16; c++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(r[c]) : "d"(a), "d"(b));
+    }
+  }
+  double acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc += r[i];
+  if (acc == 0.12345) sink[0] = 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
@@ -1416,6 +1436,7 @@ int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int thre
       case 10: k_pipe_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
       case 11: k_pipe_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
       case 12: k_pipe_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
+      case 13: k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
       default: return SYLOW_B200_ERR_ARG;
     }
     LAUNCHED(ctx);

@@ -15,6 +15,15 @@
 #ifndef SY_SMALL_CODE
 #define SY_SMALL_CODE 0
 #endif
+// SY_FORCE_INLINE_FP2=1 inlines the Fp2 product/square into their callers (bigger scheduling regions)
+#ifndef SY_FORCE_INLINE_FP2
+#define SY_FORCE_INLINE_FP2 0
+#endif
+#if SY_FORCE_INLINE_FP2
+#define SY_HD_MUL2 SY_HD
+#else
+#define SY_HD_MUL2 SY_HD_NOINLINE
+#endif
 #if SY_SMALL_CODE
 #define SY_HD_ADD SY_HD_NOINLINE
 #else
@@ -62,7 +71,7 @@ SY_HD_ADD Fp2 fp2_mul_xi(const Fp2& a) {
 //   c0 = a0 b0 - a1 b1            in (-p^2, p^2): add p*R when negative, then < p*R
 //   c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0   in [0, 2 p^2) subset [0, p*R)
 // The sums a0+a1, b0+b1 are NOT reduced (< 2p < 2^255, product < 4 p^2 < 2^510).
-SY_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
 #if SY_LAZY_FP2
   uint32_t t0[16], t1[16], t2[16], sa[8], sb[8];
   fp_mul_wide(t0, a.c0.l, b.c0.l);
@@ -89,7 +98,7 @@ SY_HD_NOINLINE Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
 // fp2.rs:164-171: ((a0+a1)(a0-a1), 2 a0 a1).  The factors a0+a1 and a0-a1+p are left unreduced
 // (< 2p each, product < 4p^2 < p*R, which is all fp_mul needs) and 2 a0 a1 is doubled before its single
 // reduction (2 a0 a1 < 2p^2 < p*R).
-SY_HD_NOINLINE Fp2 fp2_sqr(const Fp2& a) {
+SY_HD_MUL2 Fp2 fp2_sqr(const Fp2& a) {
 #if SY_LAZY_FP2
   Fp s, d, pp;
 #pragma unroll

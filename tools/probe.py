@@ -14,8 +14,9 @@ eng = sylow_b200.Engine(0)
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 res = {"sms": sms, "name": torch.cuda.get_device_name(0), "probes": []}
 names = {0: "fp_mul x1 chain", 1: "fp_mul x2 chains", 2: "fp_mul x4 chains", 10: "mad.wide.u32 independent",
-         11: "mad.lo.u32 (32-bit IMAD)", 12: "mad.lo.cc/madc.hi.cc chains (IMAD.WIDE.U32.X)"}
-for variant in (12, 10, 11, 0, 1, 2):
+         11: "mad.lo.u32 (32-bit IMAD)", 12: "mad.lo.cc/madc.hi.cc chains (IMAD.WIDE.U32.X)",
+         13: "fma.rn.f64 independent (FP64 pipe)"}
+for variant in (12, 13, 10, 11, 0, 1, 2):
     for threads, bps in ((128, 1), (128, 2), (256, 2), (256, 4), (256, 8), (512, 4)):
         iters = 4000 if variant >= 10 else 3000
         best = 0.0
