@@ -30,6 +30,9 @@ using namespace sylow;
 #endif
 #define SY_MUL_THREADS 256
 #define SY_HASH_THREADS 256
+#ifndef SY_G1_MINB
+#define SY_G1_MINB 2  // resident 256-thread blocks per SM for the Fp-only kernels (G1 ladder, hash-to-curve)
+#endif
 #define SY_SMALL_THREADS 128
 
 struct DstPrime {
@@ -183,7 +186,7 @@ k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
   ok[c] = one ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(SY_MUL_THREADS, 1)
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
 k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                      const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
                      uint8_t* __restrict__ out_inf) {
@@ -214,7 +217,7 @@ k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
 }
 
 // out[i] = affine(+-hash_to_curve(msg_i)); status[i] = 1 if the SvdW sqrt check failed
-__global__ void __launch_bounds__(SY_HASH_THREADS, 1)
+__global__ void __launch_bounds__(SY_HASH_THREADS, SY_G1_MINB)
 k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
              const __grid_constant__ DstPrime dst, int negate, uint8_t* __restrict__ out,
              uint8_t* __restrict__ out_inf, int* __restrict__ fail_flag) {
@@ -547,6 +550,7 @@ struct sylow_b200_ctx {
   int* d_fail = nullptr;
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
   DevBuf tables;
+  unsigned glued_attr_mask = 0;
 };
 
 static int fail_cuda(sylow_b200_ctx* ctx, cudaError_t e) {
@@ -796,11 +800,12 @@ template <int NV, int NF>
 static int launch_glued(sylow_b200_ctx* ctx, const uint8_t* g1v, size_t sv, const uint8_t* g1v_inf, const uint8_t* g2v,
                         const uint8_t* g2v_inf, const uint8_t* g1f, size_t sf, const uint8_t* g1f_inf,
                         const uint8_t* tables, size_t n, uint8_t* f_out, cudaStream_t s) {
-  static bool attr_done = false;  // per instantiation; setting it twice is harmless
+  // the opt-in for > 48 KB of dynamic shared memory is per device: remember it per context
   size_t smem = (size_t)NF * SY_TABLE_BYTES;
-  if (!attr_done) {
+  unsigned bit = 1u << (NV * 4 + NF);
+  if (!(ctx->glued_attr_mask & bit)) {
     CK(cudaFuncSetAttribute(k_glued<NV, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    ctx->glued_attr_mask |= bit;
   }
   k_glued<NV, NF><<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, smem, s>>>(g1v, sv, g1v_inf, g2v, g2v_inf, g1f, sf,
                                                                               g1f_inf, tables, n, f_out);

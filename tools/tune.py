@@ -32,6 +32,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     d_g2 = torch.empty((n, 128), dtype=torch.uint8, device=dev)
     eng.g1_mul_batch_dev(torch.from_numpy(g1).to(dev), torch.from_numpy(k[:n]).to(dev), d_g1)
     eng.g2_mul_batch_dev(torch.from_numpy(g2).to(dev), torch.from_numpy(k[n:]).to(dev), d_g2)
+    d_k = torch.from_numpy(k[:n]).to(dev)
+    d_g1o = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    d_msgs = torch.from_numpy(rs.randint(0, 256, size=n * 32, dtype=np.uint8)).to(dev)
+    d_offs = torch.from_numpy((np.arange(n + 1, dtype=np.int64) * 32)).to(dev)
     d_f = torch.empty((n, 384), dtype=torch.uint8, device=dev)
     d_o = torch.empty((n, 384), dtype=torch.uint8, device=dev)
 
@@ -48,10 +52,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
 
     ms_m = t(lambda: eng.miller_loop_batch_dev(d_g1, d_g2, d_f))
     ms_f = t(lambda: eng.final_exp_batch_dev(d_f, d_o))
+    # Fp-only kernels: G1 ladder and hash-to-curve
+    ms_g1 = t(lambda: eng.g1_mul_batch_dev(d_g1, torch.from_numpy(k[:n]).to(dev) if False else d_k, d_g1o))
+    ms_h = t(lambda: eng.hash_to_g1_batch_dev(d_msgs, d_offs, d_g1o))
     chk = int(d_o[:64].to(torch.int64).sum().item())
     print(json.dumps({"lib": os.environ.get("SYLOW_B200_LIB"), "n": n, "ms_miller": ms_m, "ms_fexp": ms_f,
                       "miller_per_s": n / ms_m * 1e3, "fexp_per_s": n / ms_f * 1e3,
-                      "pairings_per_s": n / (ms_m + ms_f) * 1e3, "chk": chk}))
+                      "pairings_per_s": n / (ms_m + ms_f) * 1e3, "g1_mul_per_s": n / ms_g1 * 1e3,
+                      "hash_per_s": n / ms_h * 1e3, "chk": chk}))
 else:
     log2n = sys.argv[1] if len(sys.argv) > 1 else "18"
     libs = sorted(glob.glob(os.path.join(ROOT, "build", "variants", "*.so")))
