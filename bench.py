@@ -26,6 +26,11 @@ sys.path.insert(0, ROOT)
 LIMB_PRODUCTS_PER_FP_MUL = 136        # 8-limb CIOS: 64 (a*b) + 64 (m*p) + 8 (m)        SURVEY.md 8(d)
 FP_MUL_MILLER_FUSED = 8444            # fused Miller loop, per pair                     SURVEY.md 8(d)
 FP_MUL_FINAL_EXP = 8822 + 380         # final exponentiation + one Fermat inversion     SURVEY.md 8(d)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_miller launch at 2^20 pairs, from the committed
+# `ncu --set full` capture profiles/r01e_k_miller_2pow20.json (local-memory frame spill traffic; the
+# algorithmic bytes are 576 B per pairing: this kernel is bound by the integer-multiply pipe, not by HBM - the
+# 97.5 GB are evictions of the 2.8 KB/thread frame from L2, 474 GB/s or 7 % of the measured HBM bandwidth).
+NCU_DRAM_BYTES_K_MILLER_2POW20 = 97.52e9
 
 
 def parse():
@@ -35,10 +40,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20, help="log2 of pairings per GPU per step")
-    ap.add_argument("--verify-log2n", type=int, default=18, help="log2 of signatures for the verify_batch leg (0 = skip)")
+    ap.add_argument("--verify-log2n", type=int, default=20, help="log2 of signatures for the verify_batch leg (0 = skip)")
     ap.add_argument("--extras", type=int, default=1, help="also time the Groth16-shaped check and scalar-mul configs")
     ap.add_argument("--groth-log2n", type=int, default=18)
-    ap.add_argument("--mul-log2n", type=int, default=20)
+    ap.add_argument("--mul-log2n", type=int, default=22)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -363,7 +368,10 @@ def main():
             "roofline": {"bound": "imad", "kernel": "k_miller (fused Miller loop)",
                          "achieved": lp_miller / 1e12, "peak": peak_limb_products / 1e12,
                          "unit": "T limb-products/s (32x32->64 multiply-adds)",
-                         "frac": lp_miller / peak_limb_products, "traffic": None,
+                         "frac": lp_miller / peak_limb_products,
+                         "traffic": NCU_DRAM_BYTES_K_MILLER_2POW20 if args.log2n == 20 else None,
+                         "traffic_note": "bytes per k_miller launch from profiles/r01e (ncu --set full); algorithmic "
+                                         "bytes per launch = n * 576",
                          "peak_source": "measured live: IMAD.WIDE.U32.X carry-chain probe on all SMs",
                          "ms_per_launch": ms_miller,
                          "hbm_gbs_load_store": n * (192 + 384) / (ms_miller * 1e-3) / 1e9,

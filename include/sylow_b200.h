@@ -38,7 +38,7 @@ typedef struct sylow_b200_ctx sylow_b200_ctx;
 
 typedef enum {
   SYLOW_B200_OK = 0,
-  SYLOW_B200_ERR_ARG = -1,            /* NULL pointer, bad size, unsupported hash id, DST > 255 bytes */
+  SYLOW_B200_ERR_ARG = -1,            /* NULL pointer, bad size, unsupported hash id or shape */
   SYLOW_B200_ERR_CUDA = -2,           /* CUDA runtime error (see sylow_b200_last_cuda_error) */
   SYLOW_B200_ERR_NOT_ON_CURVE = -3,   /* GroupError::NotOnCurve      (groups/group.rs:37-47) */
   SYLOW_B200_ERR_NOT_IN_SUBGROUP = -4,/* GroupError::NotInSubgroup */
@@ -48,6 +48,7 @@ typedef enum {
 } sylow_b200_status;
 
 #define SYLOW_B200_HASH_KECCAK256 0   /* XMDExpander::<Keccak256>, lib.rs:181,225 */
+#define SYLOW_B200_HASH_SHA256 1      /* XMDExpander::<Sha256>, the digest of the reference's RFC 9380 vectors */
 
 /* Context: owns one stream and growable device/pinned staging buffers on `device_id`. */
 int sylow_b200_create(sylow_b200_ctx** out, int device_id);
@@ -166,6 +167,16 @@ int sylow_b200_gt_mul_batch(sylow_b200_ctx* ctx, const uint8_t* gt /* n*384 */, 
 int sylow_b200_hash_to_g1_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets /* n+1 */, size_t n,
                                 const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out /* n*64 */,
                                 uint8_t* out_inf /* may be NULL */);
+
+/* The `Expander` trait (hasher.rs:55-129) for XMDExpander<D>, D in {Keccak-256, SHA-256}, security parameter 128;
+ * a DST longer than 255 bytes is replaced by H("H2C-OVERSIZE-DST-" || DST) as XMDExpander::new does (:157-172).
+ * expand_message: out[i] = len_in_bytes bytes (ceil(len/32) <= 255, hasher.rs:201-250);
+ * hash_to_field: out[i] = two canonical Fp (count 2, L 48, hasher.rs:84-128). */
+int sylow_b200_expand_message_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                    const uint8_t* dst, size_t dst_len, int hash_id, size_t len_in_bytes,
+                                    uint8_t* out /* n*len_in_bytes */);
+int sylow_b200_hash_to_field_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                   const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out /* n*64 */);
 
 /* sigs[i] = affine(sign(sk[i], msg_i)) = sk[i] * H(msg_i)   (lib.rs:179-187). */
 int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks /* n*32 */, const uint8_t* msgs,

@@ -13,6 +13,7 @@ _lib = None
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOT_ON_CURVE, ERR_NOT_IN_SUBGROUP, ERR_CANNOT_HASH, ERR_DECODE, ERR_NOMEM = range(-1, -8, -1)
 HASH_KECCAK256 = 0
+HASH_SHA256 = 1
 
 # every symbol include/sylow_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _P = c_void_p
@@ -44,6 +45,8 @@ _SIGNATURES = {
     "sylow_b200_g1_mul_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_g2_mul_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_hash_to_g1_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P]),
+    "sylow_b200_expand_message_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, c_size_t, _P]),
+    "sylow_b200_hash_to_field_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
     "sylow_b200_sign_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
     "sylow_b200_verify_each": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
     "sylow_b200_verify_batch_partial": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),

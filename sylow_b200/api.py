@@ -277,15 +277,33 @@ class Engine:
             return np.ascontiguousarray(buf, dtype=np.uint8), np.ascontiguousarray(offs, dtype=np.uint64)
         return pack_messages(msgs)
 
-    def hash_to_g1_batch(self, msgs, dst: bytes = DST):
+    def hash_to_g1_batch(self, msgs, dst: bytes = DST, hash_id: int = _lib.HASH_KECCAK256):
         buf, offs = self._msgs(msgs)
         n = offs.size - 1
         out = np.empty((n, 64), dtype=np.uint8)
         out_inf = np.empty(n, dtype=np.uint8)
         self._ck(self._lib.sylow_b200_hash_to_g1_batch(self._h, _ptr(buf), _ptr(offs), n, dst, len(dst),
-                                                       _lib.HASH_KECCAK256, _ptr(out), _ptr(out_inf)),
+                                                       hash_id, _ptr(out), _ptr(out_inf)),
                  "hash_to_g1_batch")
         return out, out_inf
+
+    def expand_message_batch(self, msgs, dst: bytes, len_in_bytes: int, hash_id: int = _lib.HASH_KECCAK256) -> np.ndarray:
+        """Expander::expand_message (XMD) per message: (n, len_in_bytes) uint8."""
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        out = np.empty((n, int(len_in_bytes)), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_expand_message_batch(self._h, _ptr(buf), _ptr(offs), n, dst, len(dst), hash_id,
+                                                           int(len_in_bytes), _ptr(out)), "expand_message_batch")
+        return out
+
+    def hash_to_field_batch(self, msgs, dst: bytes = DST, hash_id: int = _lib.HASH_KECCAK256) -> np.ndarray:
+        """Expander::hash_to_field(msg, 2, 48): (n, 64) = two canonical Fp per message."""
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        out = np.empty((n, 64), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_hash_to_field_batch(self._h, _ptr(buf), _ptr(offs), n, dst, len(dst), hash_id,
+                                                          _ptr(out)), "hash_to_field_batch")
+        return out
 
     def sign_batch(self, sks, msgs, dst: bytes = DST) -> np.ndarray:
         sks = _u8(sks, 32, "sks")

@@ -95,6 +95,105 @@ SY_HD void keccak_final(Keccak256& k, uint8_t* out32) {
   for (int i = 0; i < 32; i++) out32[i] = (uint8_t)(k.s[i >> 3] >> ((i & 7) * 8));
 }
 
+// ---- SHA-256 (FIPS 180-4), for XMDExpander::<Sha256> (the hash of the reference's RFC 9380 vectors, hasher.rs:430-470)
+SY_DEFINE_TABLE(uint32_t, kSha256K, 64, 0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4,
+                0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+                0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152,
+                0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138,
+                0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70,
+                0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5,
+                0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa,
+                0xa4506ceb, 0xbef9a3f7, 0xc67178f2)
+SY_HD uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+struct Sha256 {
+  static constexpr int kBlock = 64;
+  uint32_t h[8];
+  uint8_t buf[64];
+  uint64_t total;
+  int pos;
+};
+SY_HD_NOINLINE void sha256_compress(Sha256& s) {
+  uint32_t w[64];
+  for (int i = 0; i < 16; i++)
+    w[i] = ((uint32_t)s.buf[4 * i] << 24) | ((uint32_t)s.buf[4 * i + 1] << 16) | ((uint32_t)s.buf[4 * i + 2] << 8) | s.buf[4 * i + 3];
+  for (int i = 16; i < 64; i++) {
+    uint32_t s0 = rotr32(w[i - 15], 7) ^ rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+    uint32_t s1 = rotr32(w[i - 2], 17) ^ rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+    w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+  }
+  uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], hh = s.h[7];
+  for (int i = 0; i < 64; i++) {
+    uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+    uint32_t ch = (e & f) ^ (~e & g);
+    uint32_t t1 = hh + S1 + ch + SY_TAB(kSha256K)[i] + w[i];
+    uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+    uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+    uint32_t t2 = S0 + mj;
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += hh;
+}
+SY_HD void hash_init(Sha256& s) {
+  const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  for (int i = 0; i < 8; i++) s.h[i] = iv[i];
+  s.total = 0;
+  s.pos = 0;
+}
+SY_HD void hash_absorb_byte(Sha256& s, uint8_t b) {
+  s.buf[s.pos++] = b;
+  s.total++;
+  if (s.pos == 64) {
+    sha256_compress(s);
+    s.pos = 0;
+  }
+}
+SY_HD void hash_final(Sha256& s, uint8_t* out32) {
+  uint64_t bits = s.total * 8;
+  hash_absorb_byte(s, 0x80);
+  while (s.pos != 56) hash_absorb_byte(s, 0);
+  for (int i = 7; i >= 0; i--) hash_absorb_byte(s, (uint8_t)(bits >> (8 * i)));
+  for (int i = 0; i < 8; i++) {
+    out32[4 * i] = (uint8_t)(s.h[i] >> 24);
+    out32[4 * i + 1] = (uint8_t)(s.h[i] >> 16);
+    out32[4 * i + 2] = (uint8_t)(s.h[i] >> 8);
+    out32[4 * i + 3] = (uint8_t)s.h[i];
+  }
+}
+// the same three verbs for Keccak-256 so the expander below is generic over the digest (the `D` of XMDExpander<D>)
+struct Keccak256H : Keccak256 {
+  static constexpr int kBlock = 136;
+};
+SY_HD void hash_init(Keccak256H& k) { keccak_init(k); }
+SY_HD void hash_absorb_byte(Keccak256H& k, uint8_t b) { keccak_absorb_byte(k, b); }
+SY_HD void hash_final(Keccak256H& k, uint8_t* out32) { keccak_final(k, out32); }
+
+// XMDExpander::expand_message (hasher.rs:201-250) for any output length up to 255 * 32 bytes; both digests
+// have b_in_bytes = 32.  dst_prime = DST' || I2OSP(len(DST'), 1) prepared by the caller.
+template <class H>
+SY_HD_NOINLINE void expand_message_xmd(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len,
+                                       uint32_t len_in_bytes, uint8_t* out) {
+  H k;
+  uint8_t b0[32], bi[32];
+  hash_init(k);
+  for (int i = 0; i < H::kBlock; i++) hash_absorb_byte(k, 0);  // Z_pad
+  for (size_t i = 0; i < msg_len; i++) hash_absorb_byte(k, msg[i]);
+  hash_absorb_byte(k, (uint8_t)(len_in_bytes >> 8));
+  hash_absorb_byte(k, (uint8_t)len_in_bytes);
+  hash_absorb_byte(k, 0);
+  for (size_t i = 0; i < dst_prime_len; i++) hash_absorb_byte(k, dst_prime[i]);
+  hash_final(k, b0);
+  for (int i = 0; i < 32; i++) bi[i] = 0;
+  uint32_t ell = (len_in_bytes + 31) / 32;
+  for (uint32_t blk = 1; blk <= ell; blk++) {
+    hash_init(k);
+    for (int i = 0; i < 32; i++) hash_absorb_byte(k, b0[i] ^ bi[i]);
+    hash_absorb_byte(k, (uint8_t)blk);
+    for (size_t i = 0; i < dst_prime_len; i++) hash_absorb_byte(k, dst_prime[i]);
+    hash_final(k, bi);
+    for (uint32_t i = 0; i < 32 && 32 * (blk - 1) + i < len_in_bytes; i++) out[32 * (blk - 1) + i] = bi[i];
+  }
+}
+
 // 48 big-endian bytes -> value mod p, in Montgomery form (hasher.rs:93-111)
 SY_HD Fp fp_from_be48_mod(const uint8_t* b) {
   Fp hi = fp_zero(), lo;
@@ -111,31 +210,21 @@ SY_HD Fp fp_from_be48_mod(const uint8_t* b) {
   return fp_add(fp_mul(fp_R2(), lo), fp_mul(fp_R3(), hi));
 }
 
-// expand_message_xmd(msg, DST, 96) with Keccak-256, then two field elements.
-// dst_prime = DST || I2OSP(len(DST), 1), already assembled by the caller (<= 256 bytes).
-SY_HD_NOINLINE void hash_to_field_keccak(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime,
-                                         size_t dst_prime_len, Fp& u0, Fp& u1) {
-  Keccak256 k;
-  uint8_t b0[32], bi[32], uni[96];
-  keccak_init(k);
-  for (int i = 0; i < 136; i++) keccak_absorb_byte(k, 0);  // Z_pad = block size of Keccak-256
-  keccak_absorb(k, msg, msg_len);
-  keccak_absorb_byte(k, 0);
-  keccak_absorb_byte(k, 96);  // I2OSP(len_in_bytes = 96, 2)
-  keccak_absorb_byte(k, 0);   // I2OSP(0, 1)
-  keccak_absorb(k, dst_prime, dst_prime_len);
-  keccak_final(k, b0);
-  for (int i = 0; i < 32; i++) bi[i] = 0;
-  for (int blk = 1; blk <= 3; blk++) {
-    keccak_init(k);
-    for (int i = 0; i < 32; i++) keccak_absorb_byte(k, b0[i] ^ bi[i]);  // b_0 xor b_{i-1} (b_0 alone for i = 1)
-    keccak_absorb_byte(k, (uint8_t)blk);
-    keccak_absorb(k, dst_prime, dst_prime_len);
-    keccak_final(k, bi);
-    for (int i = 0; i < 32; i++) uni[32 * (blk - 1) + i] = bi[i];
-  }
+// hash_to_field(msg, count = 2, L = 48) (hasher.rs:84-128): expand to 96 bytes, two 48-byte big-endian values mod p.
+// hash_id: 0 = Keccak-256 (sylow's sign/verify), 1 = SHA-256.
+SY_HD_NOINLINE void hash_to_field_xmd(int hash_id, const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime,
+                                      size_t dst_prime_len, Fp& u0, Fp& u1) {
+  uint8_t uni[96];
+  if (hash_id == 1)
+    expand_message_xmd<Sha256>(msg, msg_len, dst_prime, dst_prime_len, 96, uni);
+  else
+    expand_message_xmd<Keccak256H>(msg, msg_len, dst_prime, dst_prime_len, 96, uni);
   u0 = fp_from_be48_mod(uni);
   u1 = fp_from_be48_mod(uni + 48);
+}
+SY_HD void hash_to_field_keccak(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len, Fp& u0,
+                                Fp& u1) {
+  hash_to_field_xmd(0, msg, msg_len, dst_prime, dst_prime_len, u0, u1);
 }
 
 SY_HD bool fp_is_square(const Fp& a) {  // fp.rs:625-631 (true for 0)
@@ -172,9 +261,9 @@ SY_HD_NOINLINE bool svdw_map_to_point(const Fp& u, Fp& x, Fp& y) {
 
 // g1.rs:307-331: map both field elements and add (projective result)
 SY_HD_NOINLINE bool hash_to_g1(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len,
-                               G1Proj& out) {
+                               G1Proj& out, int hash_id = 0) {
   Fp u0, u1;
-  hash_to_field_keccak(msg, msg_len, dst_prime, dst_prime_len, u0, u1);
+  hash_to_field_xmd(hash_id, msg, msg_len, dst_prime, dst_prime_len, u0, u1);
   G1Proj a, b;
   bool ok = svdw_map_to_point(u0, a.x, a.y);
   ok &= svdw_map_to_point(u1, b.x, b.y);

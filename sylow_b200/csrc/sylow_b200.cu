@@ -38,6 +38,7 @@ using namespace sylow;
 struct DstPrime {
   uint8_t b[256];
   uint32_t len;
+  int hash_id;  // 0 Keccak-256, 1 SHA-256
 };
 
 // f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
@@ -225,7 +226,7 @@ k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offs
   size_t i = i0 < n ? i0 : n - 1;
   uint64_t o0 = offsets[i], o1 = offsets[i + 1];
   G1Proj p;
-  bool ok = hash_to_g1(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, p);
+  bool ok = hash_to_g1(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, p, dst.hash_id);
   G1Aff r = proj_to_affine(p);
   if (i0 >= n) return;
   if (!ok) atomicExch(fail_flag, 1);
@@ -409,6 +410,48 @@ k_gt_pow(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ scalars, si
   Fp12 r = gt_pow(g, k.l);
   if (i0 >= n) return;
   fp12_store(out + i * 384, r);
+}
+
+
+// out[i] = expand_message_xmd(msg_i, DST, len_in_bytes)   (Expander::expand_message, hasher.rs:70,201-250)
+__global__ void k_expand_message(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
+                                 const __grid_constant__ DstPrime dst, uint32_t len_in_bytes, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o0 = offsets[i], o1 = offsets[i + 1];
+  if (dst.hash_id == 1)
+    expand_message_xmd<Sha256>(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, len_in_bytes, out + i * len_in_bytes);
+  else
+    expand_message_xmd<Keccak256H>(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, len_in_bytes, out + i * len_in_bytes);
+}
+// out[i] = hash_to_field(msg_i, 2, 48): two canonical Fp (Expander::hash_to_field, hasher.rs:84-128)
+__global__ void k_hash_to_field(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
+                                const __grid_constant__ DstPrime dst, uint8_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t o0 = offsets[i], o1 = offsets[i + 1];
+  Fp u0, u1;
+  hash_to_field_xmd(dst.hash_id, msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, u0, u1);
+  fp_store(out + i * 64, u0);
+  fp_store(out + i * 64 + 32, u1);
+}
+// DST longer than 255 bytes: DST' = H("H2C-OVERSIZE-DST-" || DST)   (XMDExpander::new, hasher.rs:157-172)
+__global__ void k_oversize_dst(const uint8_t* __restrict__ dst, size_t dst_len, int hash_id, uint8_t* __restrict__ out32) {
+  if (blockIdx.x || threadIdx.x) return;
+  const char prefix[] = "H2C-OVERSIZE-DST-";
+  if (hash_id == 1) {
+    Sha256 h;
+    hash_init(h);
+    for (int i = 0; i < 17; i++) hash_absorb_byte(h, (uint8_t)prefix[i]);
+    for (size_t i = 0; i < dst_len; i++) hash_absorb_byte(h, dst[i]);
+    hash_final(h, out32);
+  } else {
+    Keccak256H h;
+    hash_init(h);
+    for (int i = 0; i < 17; i++) hash_absorb_byte(h, (uint8_t)prefix[i]);
+    for (size_t i = 0; i < dst_len; i++) hash_absorb_byte(h, dst[i]);
+    hash_final(h, out32);
+  }
 }
 
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
@@ -756,12 +799,31 @@ int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const u
   return 0;
 }
 
-static int make_dst_prime(const uint8_t* dst, size_t dst_len, int hash_id, DstPrime& dp) {
-  if (hash_id != SYLOW_B200_HASH_KECCAK256) return SYLOW_B200_ERR_ARG;
-  if (dst_len > 255 || (dst_len && !dst)) return SYLOW_B200_ERR_ARG;  // oversize DST (hasher.rs:158-163): not yet
+static int make_dst_prime(sylow_b200_ctx* ctx, const uint8_t* dst, size_t dst_len, int hash_id, DstPrime& dp) {
+  if (hash_id != SYLOW_B200_HASH_KECCAK256 && hash_id != SYLOW_B200_HASH_SHA256) return SYLOW_B200_ERR_ARG;
+  if (dst_len && !dst) return SYLOW_B200_ERR_ARG;
   memset(dp.b, 0, sizeof(dp.b));
-  if (dst_len) memcpy(dp.b, dst, dst_len);
-  dp.b[dst_len] = (uint8_t)dst_len;  // DST || I2OSP(len, 1)   (hasher.rs:205-209)
+  dp.hash_id = hash_id;
+  if (dst_len > 255) {
+    // oversize DST (hasher.rs:158-163): hashed on the device, like every other digest of this library
+    if (!ctx) return SYLOW_B200_ERR_ARG;
+    uint8_t* d_tmp = nullptr;
+    CK(cudaMalloc(&d_tmp, dst_len + 32));
+    cudaError_t e = cudaMemcpyAsync(d_tmp + 32, dst, dst_len, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      k_oversize_dst<<<1, 32, 0, ctx->stream>>>(d_tmp + 32, dst_len, hash_id, d_tmp);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dp.b, d_tmp, 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail_cuda(ctx, e);
+    dst_len = 32;
+  } else if (dst_len) {
+    memcpy(dp.b, dst, dst_len);
+  }
+  dp.b[dst_len] = (uint8_t)dst_len;  // DST' || I2OSP(len(DST'), 1)   (hasher.rs:205-209)
   dp.len = (uint32_t)dst_len + 1;
   return 0;
 }
@@ -779,7 +841,7 @@ int sylow_b200_hash_to_g1_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_msgs, 
                                     uint8_t* d_out_inf, void* stream) {
   if (!ctx || (n && (!d_offsets || !d_out))) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
-  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   if (!n) return 0;
   return hash_launch(ctx, d_msgs, d_offsets, n, dp, 0, d_out, d_out_inf, pick(ctx, stream));
 }
@@ -855,7 +917,7 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
                                         void* stream) {
   if (!ctx || !d_f_out || (n && (!d_pks || !d_offsets || !d_sigs))) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
-  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   cudaStream_t s = pick(ctx, stream);
   if (!n) {
     CK(cudaMemcpyAsync(d_f_out, kOneCanonical, 384, cudaMemcpyHostToDevice, s));
@@ -1044,7 +1106,7 @@ int sylow_b200_hash_to_g1_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const 
                                 const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out, uint8_t* out_inf) {
   ENTER(ctx);
   DstPrime dp;
-  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   if (!n) return 0;
   if (!out) return SYLOW_B200_ERR_ARG;
   const uint8_t* dm;
@@ -1062,7 +1124,7 @@ int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks, const uint8_t
                           size_t n, const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* sigs_out) {
   ENTER(ctx);
   DstPrime dp;
-  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   if (!n) return 0;
   if (!sks || !sigs_out) return SYLOW_B200_ERR_ARG;
   const uint8_t *dm, *dk;
@@ -1083,7 +1145,7 @@ int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, con
   ENTER(ctx);
   if (!f_out) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
-  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   if (!n) {
     memcpy(f_out, kOneCanonical, 384);
     return 0;
@@ -1123,7 +1185,7 @@ int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_
                            uint8_t* ok_out) {
   ENTER(ctx);
   DstPrime dp;
-  CKS(make_dst_prime(dst, dst_len, hash_id, dp));
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   if (!n) return 0;
   if (!pks || !sigs || !ok_out) return SYLOW_B200_ERR_ARG;
   const uint8_t *dm, *dpk, *dsg;
@@ -1388,6 +1450,43 @@ int sylow_b200_gt_mul_batch(sylow_b200_ctx* ctx, const uint8_t* gt, const uint8_
   k_gt_pow<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(dg, dk, n, ctx->out.p);
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------- Expander trait
+int sylow_b200_expand_message_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                    const uint8_t* dst, size_t dst_len, int hash_id, size_t len_in_bytes, uint8_t* out) {
+  ENTER(ctx);
+  DstPrime dp;
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
+  // ell = ceil(len / 32) <= 255 and len < 2^16 (hasher.rs:211-216, i2osp(len, 2))
+  if (len_in_bytes == 0 || (len_in_bytes + 31) / 32 > 255 || len_in_bytes > 65535) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  if (!out) return SYLOW_B200_ERR_ARG;
+  const uint8_t* dm;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(reserve(ctx, ctx->out, n * len_in_bytes));
+  k_expand_message<<<nblocks(n, 128), 128, 0, ctx->stream>>>(dm, dof, n, dp, (uint32_t)len_in_bytes, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * len_in_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_hash_to_field_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
+                                   const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out) {
+  ENTER(ctx);
+  DstPrime dp;
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
+  if (!n) return 0;
+  if (!out) return SYLOW_B200_ERR_ARG;
+  const uint8_t* dm;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(reserve(ctx, ctx->out, n * 64));
+  k_hash_to_field<<<nblocks(n, 128), 128, 0, ctx->stream>>>(dm, dof, n, dp, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
 }
 

@@ -286,7 +286,7 @@ def test_error_paths(eng):
     with pytest.raises(ValueError):
         eng.pairing_batch(np.zeros((2, 64), np.uint8), np.zeros((3, 128), np.uint8))
     with pytest.raises(sylow_b200.SylowB200Error):
-        eng.hash_to_g1_batch([b"x"], dst=b"d" * 300)  # oversize DST not supported yet -> ERR_ARG, not a crash
+        eng.hash_to_g1_batch([b"x"], hash_id=7)  # unknown digest -> ERR_ARG, not a crash
     assert eng.pairing_batch(np.zeros((0, 64), np.uint8), np.zeros((0, 128), np.uint8)).shape == (0, 384)
     assert eng.launch_count > 0
 
@@ -474,3 +474,26 @@ def test_gt_mul_bilinearity(eng):
     # -1 * a + a == identity (additive notation)
     assert w.b_fp12(bytes(a[n - 1])) == o.fp12_conj(o.pairing_affine(ps[n - 1], qs[n - 1]))
     assert w.b_fp12(bytes(a[n - 2])) == o.FP12_ONE
+
+
+def test_expander_rfc9380_vectors(eng, kats):
+    """The reference's own expand_message vectors (src/hasher.rs:367-388,430-470): XMD-SHA256, short and
+    oversize DST, len_in_bytes = 0x20 - plus Keccak-256 and longer outputs against the oracle."""
+    from sylow_b200 import _lib
+
+    for name in ("xmd_sha256_short", "xmd_sha256_long_dst"):
+        t = kats[name]
+        msgs = [m.encode() for m, _ in t["vectors"]]
+        out = eng.expand_message_batch(msgs, t["dst"].encode(), t["len_in_bytes"], hash_id=_lib.HASH_SHA256)
+        assert [bytes(r).hex() for r in out] == [e for _, e in t["vectors"]]
+    rng = random.Random(26)
+    msgs = [b"", b"abc", bytes(rng.randrange(256) for _ in range(300))]
+    for hid, name in ((_lib.HASH_KECCAK256, "keccak256"), (_lib.HASH_SHA256, "sha256")):
+        for dst in (o.DST, b"Q" * 256):
+            for ln in (32, 96, 200):
+                out = eng.expand_message_batch(msgs, dst, ln, hash_id=hid)
+                assert [bytes(r) for r in out] == [o.expand_message_xmd(m, dst, ln, name) for m in msgs]
+            f = eng.hash_to_field_batch(msgs, dst, hash_id=hid)
+            assert [[w.b_fp(bytes(r[:32])), w.b_fp(bytes(r[32:]))] for r in f] == [o.hash_to_field(m, dst, 2, 48, name) for m in msgs]
+            pts, _ = eng.hash_to_g1_batch(msgs, dst, hash_id=hid)
+            assert [w.b_g1(bytes(r)) for r in pts] == [o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m, dst, name)) for m in msgs]

@@ -199,3 +199,21 @@ def test_gt_pow(hs):
     for k in (0, 1, 2, o.R_ORDER - 1, rng.randrange(o.R_ORDER)):
         hs.hs_gt_pow(w.fp12_b(g), w.fp_b(k), out)
         assert w.b_fp12(out.raw) == o.gt_mul(g, k)
+
+
+def test_expander_generic(hs, kats):
+    """XMD over SHA-256 (the reference's RFC 9380 vectors, hasher.rs:367-376) and Keccak-256, several lengths."""
+    hs.hs_expand.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                             ctypes.c_uint32, ctypes.c_char_p]
+    t = kats["xmd_sha256_short"]
+    dp = t["dst"].encode() + bytes([len(t["dst"])])
+    for m, e in t["vectors"]:
+        out = ctypes.create_string_buffer(32)
+        hs.hs_expand(1, m.encode(), len(m), dp, len(dp), 32, out)
+        assert out.raw.hex() == e
+    dp = o.DST + bytes([len(o.DST)])
+    for hid, name in ((0, "keccak256"), (1, "sha256")):
+        for ln in (32, 96, 177):
+            out = ctypes.create_string_buffer(ln)
+            hs.hs_expand(hid, b"abcdef" * 30, 180, dp, len(dp), ln, out)
+            assert out.raw == o.expand_message_xmd(b"abcdef" * 30, o.DST, ln, name)
