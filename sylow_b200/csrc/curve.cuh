@@ -14,6 +14,7 @@ namespace sylow {
 SY_HD Fp f_add(const Fp& a, const Fp& b) { return fp_add(a, b); }
 SY_HD Fp f_sub(const Fp& a, const Fp& b) { return fp_sub(a, b); }
 SY_HD Fp f_mul(const Fp& a, const Fp& b) { return fp_mul(a, b); }
+SY_HD Fp f_sqr(const Fp& a) { return fp_sqr(a); }
 SY_HD Fp f_mul_b3(const Fp& a) { return fp_mul9(a); }  // 3b = 9
 SY_HD Fp f_neg(const Fp& a) { return fp_neg(a); }
 SY_HD bool f_is_zero(const Fp& a) { return fp_is_zero(a); }
@@ -24,6 +25,7 @@ SY_HD Fp f_inv(const Fp& a) { return fp_inv(a); }
 SY_HD Fp2 f_add(const Fp2& a, const Fp2& b) { return fp2_add(a, b); }
 SY_HD Fp2 f_sub(const Fp2& a, const Fp2& b) { return fp2_sub(a, b); }
 SY_HD Fp2 f_mul(const Fp2& a, const Fp2& b) { return fp2_mul(a, b); }
+SY_HD Fp2 f_sqr(const Fp2& a) { return fp2_sqr(a); }
 SY_HD Fp2 f_mul_b3(const Fp2& a) { return fp2_mul(a, SY_TAB(kTwistB3)[0]); }
 SY_HD Fp2 f_neg(const Fp2& a) { return fp2_neg(a); }
 SY_HD bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
@@ -59,12 +61,12 @@ SY_HD Proj<F> proj_zero() {
 // value of the affine result; the reference's select only normalises the representative.
 template <class F>
 SY_HD_NOINLINE Proj<F> proj_double(const Proj<F>& p) {
-  F t0 = f_mul(p.y, p.y);
+  F t0 = f_sqr(p.y);
   F z3 = f_add(t0, t0);
   z3 = f_add(z3, z3);
   z3 = f_add(z3, z3);
   F t1 = f_mul(p.y, p.z);
-  F t2 = f_mul(p.z, p.z);
+  F t2 = f_sqr(p.z);
   t2 = f_mul_b3(t2);
   F x3 = f_mul(t2, z3);
   F y3 = f_add(t0, t2);
