@@ -160,6 +160,14 @@ int sylow_b200_g2_mul_batch(sylow_b200_ctx* ctx, const uint8_t* pts /* n*128 */,
 int sylow_b200_gt_mul_batch(sylow_b200_ctx* ctx, const uint8_t* gt /* n*384 */, const uint8_t* scalars /* n*32 */,
                             size_t n, uint8_t* out /* n*384 */);
 
+/* out = sum_i pts[i] (affine + infinity flag): signature aggregation.  sylow_b200_g1_msm = sum_i scalars[i] * pts[i]
+ * (Lagrange-weighted aggregation of examples/dkg.rs:190-236) as a batch of ladders plus the same tree sum - a
+ * straightforward MSM, not a bucket method. */
+int sylow_b200_g1_sum(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf, size_t n,
+                      uint8_t out[64], uint8_t* out_inf);
+int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf,
+                      const uint8_t* scalars /* n*32 */, size_t n, uint8_t out[64], uint8_t* out_inf);
+
 /* ---- hash to curve / BLS ------------------------------------------------------------------------ */
 
 /* out[i] = affine(G1Projective::hash_to_curve(XMDExpander::<Keccak256>::new(dst, 128), msg_i))
@@ -189,11 +197,19 @@ int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks /* n*128 */, 
                            const uint64_t* offsets, const uint8_t* sigs /* n*64 */, size_t n, const uint8_t* dst,
                            size_t dst_len, int hash_id, uint8_t* ok_out);
 
-/* f_out = prod_i miller(sig_i, G2gen) * miller(-H(msg_i), pk_i): this GPU's 384-byte share of the
- * batch check of examples/verify_multiple_messages_same_signer.rs:40-60. */
+/* f_out = miller(sum_i sig_i, G2gen) * prod_i miller(-H(msg_i), pk_i): this GPU's 384-byte share of the batch check of
+ * examples/verify_multiple_messages_same_signer.rs:40-60.  (prod_i e(sig_i, G2gen) = e(sum_i sig_i, G2gen), so the
+ * product of all shares has the same final exponentiation as the reference's 2n-pair glued loop.) */
 int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs,
                                     const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
                                     size_t dst_len, int hash_id, uint8_t f_out[384]);
+
+/* The reference example's exact setting - many messages, ONE signer (examples/verify_multiple_messages_same_signer.rs:
+ * 40-60): prod e(sig_i, G2gen) e(-H(m_i), pk) = e(sum sig_i, G2gen) e(-sum H(m_i), pk), i.e. n hashes, 2n point
+ * additions and two Miller loops for the whole batch.  Same verdict as the product form. */
+int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk /* 128 */, const uint8_t* msgs,
+                                        const uint64_t* offsets, const uint8_t* sigs /* n*64 */, size_t n,
+                                        const uint8_t* dst, size_t dst_len, int hash_id, int* ok);
 
 /* *ok = (final_exponentiation(prod_i partials[i]) == Gt::identity()).  n_partials = number of GPUs. */
 int sylow_b200_verify_batch_finish(sylow_b200_ctx* ctx, const uint8_t* partials /* n_partials*384 */,

@@ -269,7 +269,40 @@ class Engine:
         self._ck(self._lib.sylow_b200_gt_mul_batch(self._h, _ptr(gt), _ptr(scalars), gt.shape[0], _ptr(out)), "gt_mul_batch")
         return out
 
+    def g1_sum(self, pts, pts_inf=None):
+        """sum of the points (signature aggregation): (64-byte affine point, infinity flag)."""
+        pts = _u8(pts, 64, "pts")
+        n = pts.shape[0]
+        pts_inf = None if pts_inf is None else np.ascontiguousarray(pts_inf, dtype=np.uint8).reshape(n)
+        out = np.empty(64, dtype=np.uint8)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_g1_sum(self._h, _ptr(pts), _ptr(pts_inf), n, _ptr(out), _ptr(inf)), "g1_sum")
+        return out, int(inf[0])
+
+    def g1_msm(self, pts, scalars, pts_inf=None):
+        """sum_i scalars[i] * pts[i] (Lagrange-weighted aggregation)."""
+        pts = _u8(pts, 64, "pts")
+        scalars = _u8(scalars, 32, "scalars")
+        n = pts.shape[0]
+        pts_inf = None if pts_inf is None else np.ascontiguousarray(pts_inf, dtype=np.uint8).reshape(n)
+        out = np.empty(64, dtype=np.uint8)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_g1_msm(self._h, _ptr(pts), _ptr(pts_inf), _ptr(scalars), n, _ptr(out), _ptr(inf)),
+                 "g1_msm")
+        return out, int(inf[0])
+
     # ------------------------------------------------------------------ hash / BLS
+    def verify_batch_same_signer(self, pk, msgs, sigs, dst: bytes = DST) -> bool:
+        pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(128)
+        sigs = _u8(sigs, 64, "sigs")
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        ok = ctypes.c_int(0)
+        self._ck(self._lib.sylow_b200_verify_batch_same_signer(self._h, _ptr(pk), _ptr(buf), _ptr(offs), _ptr(sigs), n,
+                                                               dst, len(dst), _lib.HASH_KECCAK256, ctypes.byref(ok)),
+                 "verify_batch_same_signer")
+        return bool(ok.value)
+
     @staticmethod
     def _msgs(msgs):
         if isinstance(msgs, tuple):

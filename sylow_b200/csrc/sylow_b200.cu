@@ -454,6 +454,42 @@ __global__ void k_oversize_dst(const uint8_t* __restrict__ dst, size_t dst_len, 
   }
 }
 
+
+// out[t] = sum of in[t], in[t + T], ...  as projective points in Montgomery form (96 B each).  affine_in = 1: the
+// input is the affine wire format (64 B) with an optional infinity flag array.  Complete additions, so
+// infinities and repeated points need no special cases.
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_g1_sum_strided(const uint8_t* __restrict__ in, const uint8_t* __restrict__ in_inf, int affine_in, size_t n,
+                 uint8_t* __restrict__ out, size_t T) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  G1Proj acc = proj_zero<Fp>();
+  for (size_t i = t; i < n; i += T) {
+    G1Proj v;
+    if (affine_in) {
+      G1Aff a{fp_load(in + i * 64), fp_load(in + i * 64 + 32), in_inf && in_inf[i]};
+      v = affine_to_proj(a);
+    } else {
+      v = G1Proj{fp_load_raw(in + i * 96), fp_load_raw(in + i * 96 + 32), fp_load_raw(in + i * 96 + 64)};
+    }
+    acc = proj_add(acc, v);
+  }
+  fp_store_raw(out + t * 96, acc.x);
+  fp_store_raw(out + t * 96 + 32, acc.y);
+  fp_store_raw(out + t * 96 + 64, acc.z);
+}
+// one projective point (Montgomery form) -> affine wire format + infinity flag, optionally negated
+__global__ void k_g1_finish_sum(const uint8_t* __restrict__ in, int negate, uint8_t* __restrict__ out,
+                                uint8_t* __restrict__ out_inf) {
+  if (blockIdx.x || threadIdx.x) return;
+  G1Proj p{fp_load_raw(in), fp_load_raw(in + 32), fp_load_raw(in + 64)};
+  G1Aff r = proj_to_affine(p);
+  if (negate && !r.inf) r.y = fp_neg(r.y);
+  fp_store(out, r.x);
+  fp_store(out + 32, r.y);
+  out_inf[0] = r.inf ? 1 : 0;
+}
+
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
@@ -592,7 +628,7 @@ struct sylow_b200_ctx {
   DevBuf in_a, in_b, in_c, in_d, flag_a, flag_b, out, scratch0, scratch1, scratch2;
   int* d_fail = nullptr;
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
-  DevBuf tables;
+  DevBuf tables, sum0, sum1;
   unsigned glued_attr_mask = 0;
 };
 
@@ -666,6 +702,8 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->d_fail) cudaFree(ctx->d_fail);
   if (ctx->d_gen_table) cudaFree(ctx->d_gen_table);
   if (ctx->tables.p) cudaFree(ctx->tables.p);
+  if (ctx->sum0.p) cudaFree(ctx->sum0.p);
+  if (ctx->sum1.p) cudaFree(ctx->sum1.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -911,6 +949,36 @@ static int verify_miller_values(sylow_b200_ctx* ctx, const uint8_t* d_pks, const
                             ctx->scratch0.p, s);
 }
 
+// sum of n affine G1 points (wire format, optional infinity flags) -> one affine point + flag at d_out / d_out_inf
+// (device).  Tree of strided partial sums in projective coordinates, then one inversion.  Launched <<<1, 1>>>
+// at the end because fp_pow re-converges with __syncthreads().
+static int g1_sum_reduce(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_inf, size_t n, int negate,
+                         uint8_t* d_out, uint8_t* d_out_inf, cudaStream_t s) {
+  size_t T = n / 8;
+  if (T < 1) T = 1;
+  if (T > 148 * 512) T = 148 * 512;
+  CKS(reserve(ctx, ctx->sum0, T * 96));
+  CKS(reserve(ctx, ctx->sum1, (T / 4 + 1) * 96));
+  k_g1_sum_strided<<<nblocks(T, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_pts, d_inf, 1, n, ctx->sum0.p, T);
+  LAUNCHED(ctx);
+  uint8_t* cur = ctx->sum0.p;
+  uint8_t* nxt = ctx->sum1.p;
+  size_t m = T;
+  while (m > 1) {
+    size_t T2 = m / 4;
+    if (T2 < 1) T2 = 1;
+    k_g1_sum_strided<<<nblocks(T2, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(cur, nullptr, 0, m, nxt, T2);
+    LAUNCHED(ctx);
+    uint8_t* t = cur;
+    cur = nxt;
+    nxt = t;
+    m = T2;
+  }
+  k_g1_finish_sum<<<1, 1, 0, s>>>(cur, negate, d_out, d_out_inf);
+  LAUNCHED(ctx);
+  return 0;
+}
+
 int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
                                         const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n,
                                         const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* d_f_out,
@@ -923,9 +991,25 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
     CK(cudaMemcpyAsync(d_f_out, kOneCanonical, 384, cudaMemcpyHostToDevice, s));
     return 0;
   }
-  CKS(verify_miller_values(ctx, d_pks, d_msgs, d_offsets, d_sigs, n, dp, s));
-  CKS(reserve(ctx, ctx->scratch1, (n / 4 + 1) * 384));
-  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n, d_f_out, 0, s);
+  // prod_i e(sig_i, G2gen) = e(sum_i sig_i, G2gen): the n signature pairs collapse into ONE Miller loop against
+  // the generator (bilinearity; the Gt value after the final exponentiation is the same), so the slice costs
+  // n fused Miller loops (-H(m_i), pk_i), n point additions and one extra loop.
+  CKS(ensure_gen_table(ctx, s));
+  CKS(reserve(ctx, ctx->scratch0, (n + 1) * 384));
+  CKS(reserve(ctx, ctx->scratch1, ((n + 1) / 4 + 1) * 384));
+  CKS(reserve(ctx, ctx->scratch2, n * 65 + 256));
+  uint8_t* d_hm = ctx->scratch2.p;
+  uint8_t* d_hm_inf = d_hm + n * 64;
+  uint8_t* d_sum = d_hm + ((n * 65 + 63) / 64) * 64;  // 64 B point + flag
+  uint8_t* d_sum_inf = d_sum + 64;
+  CKS(hash_launch(ctx, d_msgs, d_offsets, n, dp, 1, d_hm, d_hm_inf, s));
+  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(d_hm, d_hm_inf, d_pks, nullptr, 1, n,
+                                                                     ctx->scratch0.p, 1);
+  LAUNCHED(ctx);
+  CKS(g1_sum_reduce(ctx, d_sigs, nullptr, n, 0, d_sum, d_sum_inf, s));
+  CKS((launch_glued<0, 1>(ctx, nullptr, 0, nullptr, nullptr, nullptr, d_sum, 1, d_sum_inf, ctx->d_gen_table, 1,
+                          ctx->scratch0.p + n * 384, s)));
+  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n + 1, d_f_out, 0, s);
 }
 
 // ------------------------------------------------------------------------------- host variants
@@ -1488,6 +1572,83 @@ int sylow_b200_hash_to_field_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, con
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(out, ctx->out.p, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------- sums / same-signer batches
+int sylow_b200_g1_sum(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf, size_t n, uint8_t out[64],
+                      uint8_t* out_inf) {
+  ENTER(ctx);
+  if (!out || !out_inf || (n && !pts)) return SYLOW_B200_ERR_ARG;
+  if (!n) {
+    memset(out, 0, 64);
+    out[32] = 1;  // GroupAffine::zero(): (0, 1, infinity)
+    *out_inf = 1;
+    return 0;
+  }
+  const uint8_t *dp, *di;
+  CKS(to_dev(ctx, ctx->in_a, pts, n * 64, &dp));
+  CKS(to_dev(ctx, ctx->flag_a, pts_inf, n, &di));
+  CKS(reserve(ctx, ctx->out, 128));
+  CKS(g1_sum_reduce(ctx, dp, di, n, 0, ctx->out.p, ctx->out.p + 64, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->out.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_inf, ctx->out.p + 64, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars, size_t n,
+                      uint8_t out[64], uint8_t* out_inf) {
+  ENTER(ctx);
+  if (!out || !out_inf || (n && (!pts || !scalars))) return SYLOW_B200_ERR_ARG;
+  if (!n) return sylow_b200_g1_sum(ctx, nullptr, nullptr, 0, out, out_inf);
+  const uint8_t *dp, *di, *dk;
+  CKS(to_dev(ctx, ctx->in_a, pts, n * 64, &dp));
+  CKS(to_dev(ctx, ctx->flag_a, pts_inf, n, &di));
+  CKS(to_dev(ctx, ctx->in_b, scalars, n * 32, &dk));
+  CKS(reserve(ctx, ctx->scratch2, n * 65));
+  CKS(reserve(ctx, ctx->out, 128));
+  CKS(sylow_b200_g1_mul_batch_dev(ctx, dp, di, dk, n, ctx->scratch2.p, ctx->scratch2.p + n * 64, nullptr));
+  CKS(g1_sum_reduce(ctx, ctx->scratch2.p, ctx->scratch2.p + n * 64, n, 0, ctx->out.p, ctx->out.p + 64, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->out.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_inf, ctx->out.p + 64, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk, const uint8_t* msgs,
+                                        const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
+                                        size_t dst_len, int hash_id, int* ok) {
+  ENTER(ctx);
+  if (!ok) return SYLOW_B200_ERR_ARG;
+  DstPrime dp;
+  CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
+  if (!n) {
+    *ok = 1;
+    return 0;
+  }
+  if (!pk || !sigs) return SYLOW_B200_ERR_ARG;
+  const uint8_t *dm, *dpk, *dsg;
+  const uint64_t* dof;
+  CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
+  CKS(to_dev(ctx, ctx->in_a, pk, 128, &dpk));
+  CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
+  // e(sum sig_i, G2gen) * e(-sum H(m_i), pk) == 1: two Miller loops for the whole batch
+  CKS(reserve(ctx, ctx->scratch2, n * 65 + 64));
+  CKS(reserve(ctx, ctx->out, 1024));
+  uint8_t* d_pairs = ctx->out.p;        // two G1 points (128 B) + two flags at +128 + the G2 pair at +256
+  uint8_t* d_flags = ctx->out.p + 128;
+  uint8_t* d_g2 = ctx->out.p + 256;     // G2gen || pk
+  uint8_t* d_ok = ctx->out.p + 512;
+  uint8_t* d_hm = ctx->scratch2.p;
+  CKS(hash_launch(ctx, dm, dof, n, dp, 0, d_hm, d_hm + n * 64, ctx->stream));
+  CKS(g1_sum_reduce(ctx, dsg, nullptr, n, 0, d_pairs, d_flags, ctx->stream));
+  CKS(g1_sum_reduce(ctx, d_hm, d_hm + n * 64, n, 1, d_pairs + 64, d_flags + 1, ctx->stream));
+  CK(cudaMemcpyAsync(d_g2, kG2GenWords, 128, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_g2 + 128, dpk, 128, cudaMemcpyDeviceToDevice, ctx->stream));
+  CKS(sylow_b200_pairing_check_batch_dev(ctx, d_pairs, d_flags, d_g2, nullptr, 2, 1, d_ok, nullptr));
+  uint8_t h_ok = 0;
+  CK(cudaMemcpyAsync(&h_ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  int st = check_hash_fail(ctx);
+  *ok = h_ok;
+  return st;
 }
 
 // ------------------------------------------------------------------------------- diagnostics

@@ -497,3 +497,40 @@ def test_expander_rfc9380_vectors(eng, kats):
             assert [[w.b_fp(bytes(r[:32])), w.b_fp(bytes(r[32:]))] for r in f] == [o.hash_to_field(m, dst, 2, 48, name) for m in msgs]
             pts, _ = eng.hash_to_g1_batch(msgs, dst, hash_id=hid)
             assert [w.b_g1(bytes(r)) for r in pts] == [o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m, dst, name)) for m in msgs]
+
+
+def test_sum_msm_and_same_signer(eng):
+    """Signature aggregation (sum), Lagrange-style MSM (examples/dkg.rs:190-236) and the same-signer batch of
+    examples/verify_multiple_messages_same_signer.rs:40-60."""
+    rng = random.Random(27)
+    n = 37
+    ps = [w.rand_g1(rng) for _ in range(n)]
+    ks = [rng.randrange(o.R_ORDER) for _ in range(n)]
+    P = arr([w.g1_b(p) for p in ps])
+    acc = o.proj_zero(o.FpOps)
+    macc = o.proj_zero(o.FpOps)
+    for p, k in zip(ps, ks):
+        acc = o.proj_add(o.FpOps, acc, o.affine_to_proj(o.FpOps, p))
+        macc = o.proj_add(o.FpOps, macc, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k))
+    out, inf = eng.g1_sum(P)
+    assert w.b_g1(bytes(out), inf) == o.proj_to_affine(o.FpOps, acc)
+    out, inf = eng.g1_msm(P, arr([w.fp_b(k) for k in ks]))
+    assert w.b_g1(bytes(out), inf) == o.proj_to_affine(o.FpOps, macc)
+    # P + (-P) and the empty sum are the point at infinity
+    out, inf = eng.g1_sum(arr([w.g1_b(ps[0]), w.g1_b(o.g1_affine_neg(ps[0]))]))
+    assert inf == 1 and w.b_g1(bytes(out))[:2] == (0, 1)
+    assert eng.g1_sum(np.zeros((0, 64), np.uint8))[1] == 1
+    # one signer, many messages
+    sk = rng.randrange(1, o.R_ORDER)
+    msgs = [bytes(rng.randrange(256) for _ in range(rng.randrange(1, 50))) for _ in range(n)]
+    SK = arr([w.fp_b(sk)] * n)
+    sigs = eng.sign_batch(SK, msgs)
+    pk, _ = eng.g2_mul_batch(arr([w.g2_b(o.G2_GEN)]), SK[:1])
+    assert eng.verify_batch_same_signer(pk[0], msgs, sigs) is True
+    assert eng.verify_batch(np.repeat(pk, n, axis=0), msgs, sigs) is True
+    bad = sigs.copy()
+    bad[5] = sigs[6]
+    assert eng.verify_batch_same_signer(pk[0], msgs, bad) is False
+    assert eng.verify_batch(np.repeat(pk, n, axis=0), msgs, bad) is False
+    pka = w.b_g2(bytes(pk[0]))
+    assert o.verify_batch([pka] * 4, msgs[:4], [w.b_g1(bytes(r)) for r in sigs[:4]]) is True
