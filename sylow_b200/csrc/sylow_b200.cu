@@ -544,6 +544,23 @@ __global__ void k_imad_probe(int iters, const uint32_t* src, uint32_t* sink) {
   if (acc == 0x12345678u) sink[0] = acc;  // practically never true; keeps the loop alive
 }
 
+// Instruction-fetch probe: the same dependent Montgomery multiplications as k_imad_probe<1>, but UNROLL copies of
+// the multiplication in the loop body (UNROLL * ~3 KB of straight-line code per iteration), to see how the
+// achieved rate depends on the instruction footprint that has to stream through the instruction caches.
+template <int UNROLL>
+__global__ void k_ifetch_probe(int iters, const uint32_t* src, uint32_t* sink) {
+  Fp x = fp_one(), y;
+  for (int i = 0; i < 8; i++) y.l[i] = src[i];
+  x.l[0] += threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < UNROLL; c++) x = fp_mul(x, y);
+  }
+  uint32_t acc = 0;
+  for (int i = 0; i < 8; i++) acc ^= x.l[i];
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
 // Raw pipe probes.  MODE 0: independent mad.wide.u32 (IMAD.WIDE.U32); MODE 1: independent 32-bit
 // mad.lo.u32 (IMAD); MODE 2: mad.lo.cc/madc.hi.cc carry chains of 4 pairs (IMAD.WIDE.U32.X with
 // predicate carries, the exact instruction form fp_mul uses).  64 multiply-adds per loop iteration.
@@ -1702,6 +1719,10 @@ int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int thre
       case 11: k_pipe_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
       case 12: k_pipe_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
       case 13: k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
+      case 20: k_ifetch_probe<4><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 4; break;
+      case 21: k_ifetch_probe<16><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 16; break;
+      case 22: k_ifetch_probe<64><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
+      case 23: k_ifetch_probe<256><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 256; break;
       default: return SYLOW_B200_ERR_ARG;
     }
     LAUNCHED(ctx);
