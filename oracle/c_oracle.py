@@ -34,7 +34,11 @@ def lib():
     if _lib is None:
         if not available():
             raise RuntimeError("oracle/_build/libsylow_oracle.so missing; run `make -C oracle`")
-        _lib = ctypes.CDLL(SO)
+        try:
+            _lib = ctypes.CDLL(SO)
+        except OSError:  # built on another machine / stale: rebuild from source here
+            subprocess.check_call(["make", "-s", "-B", "-C", HERE])
+            _lib = ctypes.CDLL(SO)
         _lib.so_verify_batch.restype = ctypes.c_int
     return _lib
 

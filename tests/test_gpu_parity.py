@@ -489,7 +489,7 @@ def test_expander_rfc9380_vectors(eng, kats):
     rng = random.Random(26)
     msgs = [b"", b"abc", bytes(rng.randrange(256) for _ in range(300))]
     for hid, name in ((_lib.HASH_KECCAK256, "keccak256"), (_lib.HASH_SHA256, "sha256")):
-        for dst in (o.DST, b"Q" * 256):
+        for dst in (o.DST, b"Q" * 256, b""):
             for ln in (32, 96, 200):
                 out = eng.expand_message_batch(msgs, dst, ln, hash_id=hid)
                 assert [bytes(r) for r in out] == [o.expand_message_xmd(m, dst, ln, name) for m in msgs]
