@@ -313,6 +313,8 @@ def main():
             ok = verify_step() and ok
         dt_v = max_over_ranks(time.perf_counter() - t0) / 2
         ms_v_kernels = time_ms(lambda: eng.verify_batch_partial_dev(d_pk, d_msgs, d_offs, d_sigs, d_part), reps=2)
+        d_hm = torch.empty((nv, 64), dtype=torch.uint8, device=dev)
+        ms_hash = time_ms(lambda: eng.hash_to_g1_batch_dev(d_msgs, d_offs, d_hm), reps=2)
         # S = 1 variant (the reference example's own setting: one signer, many messages), host-pointer call
         same_signer = None
         if world == 1:
@@ -327,6 +329,8 @@ def main():
         verify = {"verifies_per_s": world * nv / dt_v, "signatures_per_gpu": nv, "distinct_signers": nv,
                   "same_signer": same_signer,
                   "batch_ok": bool(ok), "ms_per_batch": dt_v * 1e3, "ms_partial_kernels": ms_v_kernels,
+                  "ms_hash_to_curve": ms_hash,
+                  "verifies_per_s_excl_hashing": world * nv / (max_over_ranks(dt_v * 1e3 - ms_hash) * 1e-3),
                   "note": "per GPU: hash-to-curve + one fused Miller loop per signature, signatures summed into one "
                           "Miller loop against the generator, tree product; all-gather of the 384-byte partials; one "
                           "final exponentiation per batch (device-resident inputs)"}
@@ -387,6 +391,9 @@ def main():
                                          "bytes per launch = n * 576",
                          "peak_source": "measured live: IMAD.WIDE.U32.X carry-chain probe on all SMs",
                          "ms_per_launch": ms_miller,
+                         "ncu_fmaheavy_pipe_pct": 60.7 if args.log2n == 20 else None,
+                         "ncu_note": "sm__pipe_fmaheavy_cycles_active of one k_miller launch at 2^20 pairs, "
+                                     "profiles/r01e_k_miller_2pow20.json",
                          "hbm_gbs_load_store": n * (192 + 384) / (ms_miller * 1e-3) / 1e9,
                          "final_exp": {"ms_per_launch": ms_fexp, "achieved": lp_fexp / 1e12,
                                        "frac": lp_fexp / peak_limb_products}},
