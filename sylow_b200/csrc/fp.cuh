@@ -44,7 +44,10 @@
 #ifndef SY_STAGGER
 #define SY_STAGGER 0
 #endif
-#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
+#if defined(__CUDA_ARCH__) && defined(SY_ROLE_SYNC)
+// experiment: two 128-thread roles per 256-thread block, each re-converging on its own named barrier
+#define SY_LOOP_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(1 + (threadIdx.x >> 7)))
+#elif defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
 #if SY_STAGGER > 0
 __device__ __forceinline__ void sy_stagger() {
   unsigned g = threadIdx.x >> 7;  // warp id / 4: position of this warp on its scheduler

@@ -525,6 +525,27 @@ k_fp12_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   fp12_store(out + i * 384, r);
 }
 
+#ifdef SY_ROLE_SYNC
+// EXPERIMENT (not built by default): warps 0-3 of a block run Miller loops, warps 4-7 run final exponentiations of
+// unrelated inputs, so the two warps that share a scheduler execute different code.
+__global__ void __launch_bounds__(256, 1)
+k_fused_experiment(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n, uint8_t* __restrict__ f_out,
+                   const uint8_t* __restrict__ f_in, uint8_t* __restrict__ gt_out) {
+  unsigned role = threadIdx.x >> 7;
+  size_t i0 = (size_t)blockIdx.x * 128 + (threadIdx.x & 127);
+  size_t i = i0 < n ? i0 : n - 1;
+  if (role == 0) {
+    const uint8_t* p = g1 + i * 64;
+    const uint8_t* q = g2 + i * 128;
+    Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
+    if (i0 < n) fp12_store_raw(f_out + i * 384, f);
+  } else {
+    Fp12 g = final_exponentiation(fp12_load_raw(f_in + i * 384));
+    if (i0 < n) fp12_store(gt_out + i * 384, g);
+  }
+}
+#endif
+
 // Register-resident Montgomery-multiplication throughput probe (the roofline denominator).
 template <int CHAINS>
 __global__ void k_imad_probe(int iters, const uint32_t* src, uint32_t* sink) {
@@ -1696,6 +1717,15 @@ int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, cons
   CK(cudaMemcpyAsync(out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
 }
+
+#ifdef SY_ROLE_SYNC
+int sylow_b200_fused_experiment(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* f_out,
+                                const uint8_t* f_in, uint8_t* gt_out, void* stream) {
+  k_fused_experiment<<<nblocks(n, 128), 256, 0, pick(ctx, stream)>>>(g1, g2, n, f_out, f_in, gt_out);
+  LAUNCHED(ctx);
+  return 0;
+}
+#endif
 
 int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms_out,
                           double* ops_out) {
