@@ -72,6 +72,26 @@ def test_fp12_ops(eng):
     assert dec(eng.fp12_op_batch(6, G, G)) == [o.cyclotomic_squared(g)]
 
 
+def test_fp12_edge_coefficients(eng):
+    """Carry-propagation extremes of the lazy-reduction Fp2 arithmetic: every coefficient drawn from
+    {0, 1, 2, p-1, p-2, (p-1)/2, (p+1)/2, 2^32-1, 2^224, R mod p, ...}."""
+    rng = random.Random(29)
+    edge = [0, 1, 2, o.P - 1, o.P - 2, (o.P - 1) // 2, (o.P + 1) // 2, (1 << 32) - 1, 1 << 224, (1 << 253) + 1,
+            (1 << 256) % o.P, o.P - ((1 << 256) % o.P), 0xFFFFFFFF00000000FFFFFFFF00000000FFFFFFFF00000000 % o.P]
+    n = 160
+    a = [o.fp12_from_list([rng.choice(edge) for _ in range(12)]) for _ in range(n)]
+    b = [o.fp12_from_list([rng.choice(edge) for _ in range(12)]) for _ in range(n)]
+    a[0] = o.fp12_from_list([o.P - 1] * 12)
+    b[0] = o.fp12_from_list([o.P - 1] * 12)
+    A, B = arr([w.fp12_b(x) for x in a]), arr([w.fp12_b(x) for x in b])
+    dec = lambda out: [w.b_fp12(bytes(r)) for r in out]
+    assert dec(eng.fp12_op_batch(0, A, B)) == [o.fp12_mul(x, y) for x, y in zip(a, b)]
+    assert dec(eng.fp12_op_batch(1, A, B)) == [o.fp12_sqr(x) for x in a]
+    assert dec(eng.fp12_op_batch(7, A, B)) == [o.fp12_sparse_mul(x, y[0][0], y[0][1], y[0][2]) for x, y in zip(a, b)]
+    for e in (1, 2, 3):
+        assert dec(eng.fp12_op_batch(2 + e, A, B)) == [o.fp12_frobenius(x, e) for x in a]
+
+
 # ------------------------------------------------------------------------------------------ pairing
 def test_pairing_generators_kat(eng, kats):
     """config #1: e(G1gen, G2gen) == GT, src/pairing.rs:1052-1057 / src/groups/gt.rs:20-109."""
