@@ -161,6 +161,100 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul(const Proj<F>& p, const uint32_t* k) {
   return acc;
 }
 
+// ---- GLV scalar multiplication --------------------------------------------------------------------
+// phi(x, y) = (beta x, y) is an endomorphism of both curves (j = 0) and acts on the r-torsion as
+// multiplication by lambda, lambda^2 + lambda + 1 = 0 mod r.  k = k1 + k2 lambda (mod r) with
+// |k1|, |k2| < 2^127 halves the number of doublings.  The result equals k * P as a group element for
+// every P of order r, i.e. the same affine point as the reference's loop (group.rs:639-667).
+SY_HD Fp f_mul_beta(const Fp& x) { return fp_mul(x, SY_TAB(kBetaG1)[0]); }
+SY_HD Fp2 f_mul_beta(const Fp2& x) { return fp2_mul_fp(x, SY_TAB(kBetaG2)[0]); }
+
+// t[0..NA+NB) = a * b, schoolbook on 32-bit limbs
+template <int NA, int NB>
+SY_HD void mp_mul(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  for (int i = 0; i < NA + NB; i++) t[i] = 0;
+  for (int i = 0; i < NA; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < NB; j++) {
+      uint64_t v = (uint64_t)a[i] * b[j] + t[i + j] + carry;
+      t[i + j] = (uint32_t)v;
+      carry = v >> 32;
+    }
+    t[i + NB] = (uint32_t)carry;
+  }
+}
+// r[0..8) -= a[0..n) mod 2^256
+SY_HD void mp_sub256(uint32_t* r, const uint32_t* a, int n) {
+  uint32_t borrow = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t v = (uint64_t)r[i] - (i < n ? a[i] : 0u) - borrow;
+    r[i] = (uint32_t)v;
+    borrow = (uint32_t)(v >> 63);
+  }
+}
+// two's complement 256-bit value -> magnitude (4 limbs, the bound above) and sign
+SY_HD bool mp_abs128(uint32_t* mag, const uint32_t* v) {
+  bool neg = (v[7] >> 31) != 0;
+  uint32_t carry = neg ? 1u : 0u, m = neg ? 0xFFFFFFFFu : 0u;
+  for (int i = 0; i < 4; i++) {
+    uint64_t s = (uint64_t)(v[i] ^ m) + carry;
+    mag[i] = (uint32_t)s;
+    carry = (uint32_t)(s >> 32);
+  }
+  return neg;
+}
+// Babai rounding with precomputed g_i = round(2^320 b_i / r): c_i = (k g_i) >> 320 is within one of
+// k b_i / r, so the remainders are bounded by |a1| + |a2| and |b1| + |b2| < 2^127.
+SY_HD void glv_decompose(const uint32_t* k, uint32_t* k1, bool& neg1, uint32_t* k2, bool& neg2) {
+  uint32_t t[16], c1[3], c2[5], u[9], s1[8], s2[8];
+  mp_mul<8, 5>(t, k, SY_TAB(kGlvG1));
+  for (int i = 0; i < 3; i++) c1[i] = t[10 + i];
+  mp_mul<8, 7>(t, k, SY_TAB(kGlvG2));
+  for (int i = 0; i < 5; i++) c2[i] = t[10 + i];
+  for (int i = 0; i < 8; i++) s1[i] = k[i];
+  mp_mul<3, 2>(u, c1, SY_TAB(kGlvA1));
+  mp_sub256(s1, u, 5);
+  mp_mul<5, 4>(u, c2, SY_TAB(kGlvA2));
+  mp_sub256(s1, u, 8);
+  mp_mul<3, 4>(u, c1, SY_TAB(kGlvNB1));
+  for (int i = 0; i < 8; i++) s2[i] = i < 7 ? u[i] : 0u;
+  mp_mul<5, 2>(u, c2, SY_TAB(kGlvB2));
+  mp_sub256(s2, u, 7);
+  neg1 = mp_abs128(k1, s1);
+  neg2 = mp_abs128(k2, s2);
+}
+
+// k * P = k1 * P + k2 * phi(P): one table of 0..15 multiples of P serves both halves (phi is applied to
+// the selected entry), 32 windows of 4 bits, complete additions, no data-dependent control flow.
+template <class F>
+SY_HD_NOINLINE Proj<F> proj_scalar_mul_glv(const Proj<F>& p, const uint32_t* k) {
+  uint32_t k1[4], k2[4];
+  bool neg1, neg2;
+  glv_decompose(k, k1, neg1, k2, neg2);
+  Proj<F> tab[16];
+  tab[0] = proj_zero<F>();
+  tab[1] = p;
+  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
+  Proj<F> acc = proj_zero<F>();
+  for (int w = 31; w >= 0; w--) {
+    SY_LOOP_SYNC();
+    if (w != 31) {
+      acc = proj_double(acc);
+      acc = proj_double(acc);
+      acc = proj_double(acc);
+      acc = proj_double(acc);
+    }
+    Proj<F> t = tab[(k1[w >> 3] >> ((w & 7) * 4)) & 15u];
+    if (neg1) t.y = f_neg(t.y);
+    acc = proj_add(acc, t);
+    t = tab[(k2[w >> 3] >> ((w & 7) * 4)) & 15u];
+    t.x = f_mul_beta(t.x);
+    if (neg2) t.y = f_neg(t.y);
+    acc = proj_add(acc, t);
+  }
+  return acc;
+}
+
 // y^2 == x^3 + b
 SY_HD bool g1_on_curve(const Fp& x, const Fp& y) {
   Fp rhs = fp_add(fp_mul(fp_sqr(x), x), SY_TAB(kFpThree)[0]);

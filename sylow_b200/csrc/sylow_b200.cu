@@ -16,6 +16,15 @@ using namespace sylow;
 // kernels.  One item (pair / point / message / check) per thread; control flow is uniform across
 // a warp except for the infinity early-outs and the message-length loops of the hash.
 // ------------------------------------------------------------------------------------------------
+// Scalar multiplication ladder: GLV (curve.cuh) by default; -DSY_GLV=0 restores the plain 4-bit window ladder.
+#ifndef SY_GLV
+#define SY_GLV 1
+#endif
+#if SY_GLV
+#define SY_SCALAR_MUL proj_scalar_mul_glv
+#else
+#define SY_SCALAR_MUL proj_scalar_mul
+#endif
 #ifndef SY_MILLER_THREADS
 #define SY_MILLER_THREADS 256
 #endif
@@ -195,7 +204,7 @@ k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
   size_t i = i0 < n ? i0 : n - 1;  // all threads run the (block-synchronised) loops; surplus is discarded
   G1Aff a{fp_load(pts + i * 64), fp_load(pts + i * 64 + 32), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
-  G1Aff r = proj_to_affine(proj_scalar_mul(affine_to_proj(a), k.l));
+  G1Aff r = proj_to_affine(SY_SCALAR_MUL(affine_to_proj(a), k.l));
   if (i0 >= n) return;
   fp_store(out + i * 64, r.x);
   fp_store(out + i * 64 + 32, r.y);
@@ -210,7 +219,7 @@ k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
   size_t i = i0 < n ? i0 : n - 1;
   G2Aff a{fp2_load(pts + i * 128), fp2_load(pts + i * 128 + 64), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
-  G2Aff r = proj_to_affine(proj_scalar_mul(affine_to_proj(a), k.l));
+  G2Aff r = proj_to_affine(SY_SCALAR_MUL(affine_to_proj(a), k.l));
   if (i0 >= n) return;
   fp2_store(out + i * 128, r.x);
   fp2_store(out + i * 128 + 64, r.y);

@@ -94,6 +94,32 @@ int hs_g2_mul(const uint8_t* pt, int inf, const uint8_t* k, uint8_t* out) {
   fp2_store(out + 64, r.y);
   return r.inf;
 }
+int hs_g1_mul_glv(const uint8_t* pt, int inf, const uint8_t* k, uint8_t* out) {
+  G1Aff a{fp_load(pt), fp_load(pt + 32), inf != 0};
+  Fp kk = fp_load_raw(k);
+  G1Aff r = proj_to_affine(proj_scalar_mul_glv(affine_to_proj(a), kk.l));
+  fp_store(out, r.x);
+  fp_store(out + 32, r.y);
+  return r.inf;
+}
+int hs_g2_mul_glv(const uint8_t* pt, int inf, const uint8_t* k, uint8_t* out) {
+  G2Aff a{fp2_load(pt), fp2_load(pt + 64), inf != 0};
+  Fp kk = fp_load_raw(k);
+  G2Aff r = proj_to_affine(proj_scalar_mul_glv(affine_to_proj(a), kk.l));
+  fp2_store(out, r.x);
+  fp2_store(out + 64, r.y);
+  return r.inf;
+}
+// out: |k1| (16 bytes LE), |k2| (16 bytes LE); return bit0 = k1 negative, bit1 = k2 negative
+int hs_glv_decompose(const uint8_t* k, uint8_t* out) {
+  Fp kk = fp_load_raw(k);
+  uint32_t k1[4], k2[4];
+  bool n1, n2;
+  glv_decompose(kk.l, k1, n1, k2, n2);
+  memcpy(out, k1, 16);
+  memcpy(out + 16, k2, 16);
+  return (n1 ? 1 : 0) | (n2 ? 2 : 0);
+}
 int hs_g1_add(const uint8_t* p, int pinf, const uint8_t* q, int qinf, uint8_t* out) {
   G1Aff a{fp_load(p), fp_load(p + 32), pinf != 0}, b{fp_load(q), fp_load(q + 32), qinf != 0};
   G1Aff r = proj_to_affine(proj_add(affine_to_proj(a), affine_to_proj(b)));

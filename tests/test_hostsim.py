@@ -114,6 +114,42 @@ def test_scalar_mul(hs, kats):
     assert hs.hs_g1_mul(w.g1_b((0, 1)), 1, w.fp_b(5), out) == 1 and w.b_g1(out.raw)[:2] == (0, 1)
 
 
+def test_glv_decompose(hs):
+    """k = k1 + k2 * lambda (mod r) with both halves below 2^127, for every 256-bit k."""
+    rng = random.Random(77)
+    lam = 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90DD
+    out = ctypes.create_string_buffer(32)
+    edge = [0, 1, 2, lam, lam + 1, o.R_ORDER - 1, o.R_ORDER, o.R_ORDER + 1, o.P - 1, o.P, 2**256 - 1, 2**255,
+            2**128 - 1, 2**128, 2**127]
+    for k in edge + [rng.randrange(2**256) for _ in range(3000)] + [rng.randrange(o.R_ORDER) for _ in range(1000)]:
+        s = hs.hs_glv_decompose(k.to_bytes(32, "little"), out)
+        k1 = int.from_bytes(out.raw[:16], "little") * (-1 if s & 1 else 1)
+        k2 = int.from_bytes(out.raw[16:], "little") * (-1 if s & 2 else 1)
+        assert (k1 + k2 * lam - k) % o.R_ORDER == 0, hex(k)
+        assert abs(k1) < 2**127 and abs(k2) < 2**127, hex(k)
+
+
+def test_scalar_mul_glv(hs):
+    """GLV ladder == the oracle's k * P on both groups (affine result)."""
+    rng = random.Random(78)
+    lam = 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90DD
+    p = w.rand_g1(rng)
+    out = ctypes.create_string_buffer(64)
+    ks = [0, 1, 2, 15, 16, lam, o.R_ORDER - 1, o.R_ORDER, o.R_ORDER + 1, o.P - 1, 2**256 - 1]
+    for k in ks + [rng.randrange(2**256) for _ in range(6)]:
+        inf = hs.hs_g1_mul_glv(w.g1_b(p), 0, k.to_bytes(32, "little"), out)
+        ref = o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k % o.R_ORDER))
+        assert w.b_g1(out.raw, inf) == ref, hex(k)
+    q = w.rand_g2(rng)
+    out = ctypes.create_string_buffer(128)
+    for k in ks + [rng.randrange(2**256) for _ in range(4)]:
+        inf = hs.hs_g2_mul_glv(w.g2_b(q), 0, k.to_bytes(32, "little"), out)
+        ref = o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), k % o.R_ORDER))
+        assert w.b_g2(out.raw, inf) == ref, hex(k)
+    out = ctypes.create_string_buffer(64)
+    assert hs.hs_g1_mul_glv(w.g1_b((0, 1)), 1, (5).to_bytes(32, "little"), out) == 1 and w.b_g1(out.raw)[:2] == (0, 1)
+
+
 def test_g1_add_eip196(hs, kats):
     inp = bytes.fromhex(kats["eip196_add"]["input"])
     c = [int.from_bytes(inp[32 * i: 32 * i + 32], "big") for i in range(4)]

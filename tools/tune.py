@@ -55,10 +55,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
     # Fp-only kernels: G1 ladder and hash-to-curve
     ms_g1 = t(lambda: eng.g1_mul_batch_dev(d_g1, torch.from_numpy(k[:n]).to(dev) if False else d_k, d_g1o))
     ms_h = t(lambda: eng.hash_to_g1_batch_dev(d_msgs, d_offs, d_g1o))
+    d_g2o = torch.empty((n, 128), dtype=torch.uint8, device=dev)
+    ms_g2 = t(lambda: eng.g2_mul_batch_dev(d_g2, d_k, d_g2o))
     chk = int(d_o[:64].to(torch.int64).sum().item())
     print(json.dumps({"lib": os.environ.get("SYLOW_B200_LIB"), "n": n, "ms_miller": ms_m, "ms_fexp": ms_f,
                       "miller_per_s": n / ms_m * 1e3, "fexp_per_s": n / ms_f * 1e3,
-                      "pairings_per_s": n / (ms_m + ms_f) * 1e3, "g1_mul_per_s": n / ms_g1 * 1e3,
+                      "pairings_per_s": n / (ms_m + ms_f) * 1e3, "g1_mul_per_s": n / ms_g1 * 1e3, "g2_mul_per_s": n / ms_g2 * 1e3,
                       "hash_per_s": n / ms_h * 1e3, "chk": chk}))
 else:
     log2n = sys.argv[1] if len(sys.argv) > 1 else "18"
