@@ -591,6 +591,95 @@ __global__ void k_ifetch_probe(int iters, const uint32_t* src, uint32_t* sink) {
   if (acc == 0x12345678u) sink[0] = acc;
 }
 
+// Tower-level throughput probe: `iters` dependent applications of one tower operation per thread on
+// thread-private operands, launched like the pairing kernels (256 threads, one block per SM), to see at
+// which level of the tower the limb-product rate falls below the back-to-back fp_mul rate.
+template <int OP>
+__global__ void __launch_bounds__(256, 1) k_tower_probe(int iters, const uint32_t* src, uint32_t* sink) {
+  Fp12 a, b;
+  Fp* pa = reinterpret_cast<Fp*>(&a);
+  Fp* pb = reinterpret_cast<Fp*>(&b);
+  for (int j = 0; j < 12; j++)
+    for (int i = 0; i < 8; i++) {
+      pa[j].l[i] = (src[i] + threadIdx.x * 977u + j) & (i == 7 ? 0x1FFFFFFFu : 0xFFFFFFFFu);
+      pb[j].l[i] = (src[8 + i] + threadIdx.x * 131u + j * 7u) & (i == 7 ? 0x1FFFFFFFu : 0xFFFFFFFFu);
+    }
+  G2Proj r{a.c0.c0, a.c0.c1, a.c0.c2};
+  for (int it = 0; it < iters; it++) {
+    if (OP == 0) a.c0.c0 = fp2_mul(a.c0.c0, b.c0.c0);
+    if (OP == 1) a.c0.c0 = fp2_sqr(a.c0.c0);
+    if (OP == 2) a.c0 = fp6_mul(a.c0, b.c0);
+    if (OP == 3) a = fp12_mul(a, b);
+    if (OP == 4) a = fp12_sqr(a);
+    if (OP == 5) a = fp12_sparse_mul(a, b.c0.c0, b.c0.c1, b.c0.c2);
+    if (OP == 6) a = cyclotomic_squared(a);
+    if (OP == 7) {
+      Ell e = g2_doubling_step(r);
+      a.c0.c0 = fp2_add(a.c0.c0, e.c0);
+      a.c0.c1 = fp2_add(a.c0.c1, e.c1);
+      a.c0.c2 = fp2_add(a.c0.c2, e.c2);
+    }
+    if (OP == 8) a.c0.c0 = fp2_add(fp2_sub(a.c0.c0, b.c0.c0), a.c0.c1);
+    if (OP == 9) a.c0.c0.c0 = fp_add(fp_sub(a.c0.c0.c0, b.c0.c0.c0), a.c0.c0.c1);
+  }
+  uint32_t acc = 0;
+  for (int j = 0; j < 12; j++)
+    for (int i = 0; i < 8; i++) acc ^= pa[j].l[i];
+  acc ^= r.x.c0.l[0] ^ r.y.c0.l[1] ^ r.z.c1.l[2];
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
+// Pipe-overlap probe: one fp_mul (IMAD.WIDE pipe) and eight fp additions (ALU pipe) per iteration.
+//   MODE 0: the additions are independent of the product (same basic block: the scheduler may interleave them)
+//   MODE 1: strictly alternating phases (the additions consume the product, the next product consumes the sum)
+//   MODE 2: MODE 1 with the odd warps skewed by one addition phase
+//   MODE 3: MODE 1 with the odd warps skewed by half a multiplication
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) k_overlap_probe(int iters, const uint32_t* src, uint32_t* sink) {
+  Fp x = fp_one(), y, u, v;
+  for (int i = 0; i < 8; i++) {
+    y.l[i] = src[i] & (i == 7 ? 0x1FFFFFFFu : 0xFFFFFFFFu);
+    u.l[i] = (src[8 + i] + threadIdx.x) & (i == 7 ? 0x0FFFFFFFu : 0xFFFFFFFFu);
+    v.l[i] = (src[16 + i] ^ threadIdx.x) & (i == 7 ? 0x0FFFFFFFu : 0xFFFFFFFFu);
+  }
+  x.l[0] += threadIdx.x;
+  if (MODE == 2 && ((threadIdx.x >> 5) & 1)) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      u = fp_add(fp_sub(u, v), y);
+      v = fp_sub(fp_add(v, u), y);
+    }
+  }
+  if (MODE == 3 && ((threadIdx.x >> 5) & 1)) {
+    uint32_t t = 0;
+#pragma unroll 1
+    for (int k = 0; k < 40; k++) t = t * x.l[1] + u.l[k & 7];
+    u.l[0] ^= t & 1u;
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    if (MODE == 0) {
+      x = fp_mul(x, y);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        u = fp_add(fp_sub(u, v), y);
+        v = fp_sub(fp_add(v, u), y);
+      }
+    } else {
+      x = fp_mul(u, y);
+      u = fp_add(fp_sub(x, v), y);
+      v = fp_sub(fp_add(v, u), y);
+      u = fp_add(fp_sub(u, v), y);
+      v = fp_sub(fp_add(v, u), x);
+      u = fp_add(u, v);
+      u.l[7] &= 0x1FFFFFFFu;
+    }
+  }
+  uint32_t acc = 0;
+  for (int i = 0; i < 8; i++) acc ^= x.l[i] ^ u.l[i] ^ v.l[i];
+  if (acc == 0x12345678u) sink[0] = acc;
+}
+
 // Raw pipe probes.  MODE 0: independent mad.wide.u32 (IMAD.WIDE.U32); MODE 1: independent 32-bit
 // mad.lo.u32 (IMAD); MODE 2: mad.lo.cc/madc.hi.cc carry chains of 4 pairs (IMAD.WIDE.U32.X with
 // predicate carries, the exact instruction form fp_mul uses).  64 multiply-adds per loop iteration.
@@ -1762,6 +1851,20 @@ int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int thre
       case 21: k_ifetch_probe<16><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 16; break;
       case 22: k_ifetch_probe<64><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 64; break;
       case 23: k_ifetch_probe<256><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 256; break;
+      case 30: k_tower_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 3; break;
+      case 31: k_tower_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 2; break;
+      case 32: k_tower_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 18; break;
+      case 33: k_tower_probe<3><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 54; break;
+      case 34: k_tower_probe<4><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 36; break;
+      case 35: k_tower_probe<5><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 39; break;
+      case 36: k_tower_probe<6><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 18; break;
+      case 37: k_tower_probe<7><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 26; break;
+      case 38: k_tower_probe<8><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 4; break;
+      case 39: k_tower_probe<9><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 2; break;
+      case 40: k_overlap_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
+      case 41: k_overlap_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
+      case 42: k_overlap_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
+      case 43: k_overlap_probe<3><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
       default: return SYLOW_B200_ERR_ARG;
     }
     LAUNCHED(ctx);

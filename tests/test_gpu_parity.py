@@ -214,13 +214,16 @@ def test_scalar_mul(eng, kats):
     assert w.b_g1(bytes(out[0]))[:2] == (int.from_bytes(exp[:32], "big"), int.from_bytes(exp[32:], "big")) and not inf[0]
     n = 70
     ps = [w.rand_g1(rng) for _ in range(n)]
-    ks = [0, 1, 2, o.R_ORDER, o.R_ORDER - 1, o.P - 1, (1 << 254) - 1] + [rng.randrange(o.P) for _ in range(n - 7)]
+    lam = 0xB3C4D79D41A917585BFC41088D8DAAA78B17EA66B99C90DD  # the GLV eigenvalue (curve.cuh)
+    ks = [0, 1, 2, o.R_ORDER, o.R_ORDER - 1, o.P - 1, (1 << 254) - 1, lam, lam + 1, o.R_ORDER + 1, (1 << 256) - 1,
+          1 << 255, (1 << 128) - 1, 1 << 127]
+    ks += [rng.randrange(o.P) for _ in range(n - len(ks) - 8)] + [rng.randrange(1 << 256) for _ in range(8)]
     out, inf = eng.g1_mul_batch(arr([w.g1_b(p) for p in ps]), arr([w.fp_b(k) for k in ks]))
     ref = [o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k)) for p, k in zip(ps, ks)]
     assert [w.b_g1(bytes(r), i) for r, i in zip(out, inf)] == ref
     n = 24
     qs = [w.rand_g2(rng) for _ in range(n)]
-    ks = [0, 1, o.R_ORDER - 1, o.P - 1] + [rng.randrange(o.P) for _ in range(n - 4)]
+    ks = [0, 1, o.R_ORDER - 1, o.P - 1, lam, o.R_ORDER, (1 << 256) - 1] + [rng.randrange(1 << 256) for _ in range(n - 7)]
     out, inf = eng.g2_mul_batch(arr([w.g2_b(q) for q in qs]), arr([w.fp_b(k) for k in ks]))
     ref = [o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), k)) for q, k in zip(qs, ks)]
     assert [w.b_g2(bytes(r), i) for r, i in zip(out, inf)] == ref
