@@ -8,7 +8,7 @@
 //! ```ignore
 //! mod batch;
 //! pub use crate::batch::{g1_mul_batch, g2_mul_batch, pairing_batch, pairing_check_batch, sign_batch,
-//!                        verify_batch, verify_each, Engine};
+//!                        threshold_aggregate_batch, verify_batch, verify_each, Engine};
 //! ```
 //!
 //! NOT COMPILED in the build image (no Rust toolchain); the C ABI underneath is what the parity tests
@@ -181,6 +181,22 @@ pub fn g1_mul_batch(e: &mut Engine, pts: &[G1Projective], scalars: &[Fp]) -> Res
     status(unsafe {
         sys::sylow_b200_g1_mul_batch(e.ctxs[0], g1.as_ptr(), g1i.as_ptr(), ks.as_ptr(), n, out.as_mut_ptr(),
                                      inf.as_mut_ptr())
+    })?;
+    Ok(out.chunks_exact(64).zip(&inf)
+        .map(|(b, &i)| G1Affine { x: get_fp(&b[..32]), y: get_fp(&b[32..]), infinity: Choice::from(i) })
+        .collect())
+}
+
+/// Threshold aggregation (examples/dkg.rs:190-226): `ids.len() / t` independent sets of `t` partial signatures;
+/// `out[s] = sum_i lambda_i * sigs[s*t + i]` with the Lagrange coefficients at 0 computed on the device.
+pub fn threshold_aggregate_batch(e: &mut Engine, ids: &[u64], sigs: &[G1Projective], t: usize) -> Result<Vec<G1Affine>, GroupError> {
+    assert!(t > 0 && ids.len() == sigs.len() && ids.len() % t == 0);
+    let n_sets = ids.len() / t;
+    let (sg, sgi) = marshal_g1(sigs);
+    let (mut out, mut inf) = (vec![0u8; n_sets * 64], vec![0u8; n_sets]);
+    status(unsafe {
+        sys::sylow_b200_threshold_aggregate_batch(e.ctxs[0], ids.as_ptr(), sg.as_ptr(), sgi.as_ptr(), n_sets, t,
+                                                  out.as_mut_ptr(), inf.as_mut_ptr())
     })?;
     Ok(out.chunks_exact(64).zip(&inf)
         .map(|(b, &i)| G1Affine { x: get_fp(&b[..32]), y: get_fp(&b[32..]), infinity: Choice::from(i) })

@@ -168,6 +168,19 @@ int sylow_b200_g1_sum(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const 
 int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf,
                       const uint8_t* scalars /* n*32 */, size_t n, uint8_t out[64], uint8_t* out_inf);
 
+/* Threshold-signature aggregation (examples/dkg.rs:190-226, examples/threshold_signing.rs:124-155).  A batch of
+ * `n_sets` independent aggregations of `t` shares each; ids[s*t + i] is the participant id x of share i of set s
+ * (`Fr::from(id as u64)`).
+ *   lagrange_coefficients_batch: out[s*t + i] = prod_{j != i} x_j / (x_j - x_i) mod r   (32-byte LE canonical Fr)
+ *   threshold_aggregate_batch:   out[s] = sum_i lambda[s][i] * sigs[s*t + i]             (affine + infinity flag)
+ * Fr::inv(0) = 0 as in the reference (fields/fp.rs:418-424), so a repeated id gives a zero coefficient instead of a
+ * failure; the reference's HashMap keys cannot repeat. */
+int sylow_b200_lagrange_coefficients_batch(sylow_b200_ctx* ctx, const uint64_t* ids /* n_sets*t */, size_t n_sets,
+                                           size_t t, uint8_t* out /* n_sets*t*32 */);
+int sylow_b200_threshold_aggregate_batch(sylow_b200_ctx* ctx, const uint64_t* ids /* n_sets*t */,
+                                         const uint8_t* sigs /* n_sets*t*64 */, const uint8_t* sigs_inf, size_t n_sets,
+                                         size_t t, uint8_t* out /* n_sets*64 */, uint8_t* out_inf /* n_sets */);
+
 /* ---- hash to curve / BLS ------------------------------------------------------------------------ */
 
 /* out[i] = affine(G1Projective::hash_to_curve(XMDExpander::<Keccak256>::new(dst, 128), msg_i))

@@ -102,6 +102,21 @@ class Engine {
     for (size_t i = 0; i < n; i++) { std::memcpy(&r[i].x, &out[64 * i], 64); r[i].infinity = inf[i]; }
     return r;
   }
+  // Threshold aggregation: `n_sets` sets of `t` shares; ids[s*t + i] is the participant id of share i of set s.
+  // out[s] = sum_i lambda_i * sigs[s*t + i] with the Lagrange coefficients at 0 (examples/dkg.rs:190-226).
+  std::vector<G1Affine> threshold_aggregate_batch(const std::vector<std::uint64_t>& ids,
+                                                  const std::vector<G1Affine>& sigs, size_t t) {
+    size_t n = same(ids.size(), sigs.size());
+    if (!t || n % t) throw std::invalid_argument("threshold_aggregate_batch: n must be a multiple of t");
+    size_t n_sets = n / t;
+    Packed a = pack(sigs);
+    std::vector<std::uint8_t> out(n_sets * 64), inf(n_sets);
+    ck(sylow_b200_threshold_aggregate_batch(ctx_, ids.data(), a.pts.data(), a.inf.data(), n_sets, t, out.data(),
+                                            inf.data()), "threshold_aggregate_batch");
+    std::vector<G1Affine> r(n_sets);
+    for (size_t i = 0; i < n_sets; i++) { std::memcpy(&r[i].x, &out[64 * i], 64); r[i].infinity = inf[i]; }
+    return r;
+  }
   std::vector<G2Affine> g2_mul_batch(const std::vector<G2Affine>& pts, const std::vector<Fp>& k) {
     size_t n = same(pts.size(), k.size());
     Packed a = pack(pts);

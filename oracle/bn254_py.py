@@ -939,3 +939,26 @@ def gt_mul(g, k: int):
         elif (nm >> i) & 1:
             res = fp12_mul(res, neg)
     return res
+
+
+# ---- threshold aggregation (examples/dkg.rs:190-226, examples/threshold_signing.rs:124-155) -------------------
+def lagrange_coefficients(ids):
+    """[prod_{j != i} x_j * (x_j - x_i)^-1 mod r for i], the fold of dkg.rs:216-226 (Fr::inv(0) = 0)."""
+    out = []
+    for i, xi in enumerate(ids):
+        acc = 1
+        for j, xj in enumerate(ids):
+            if j == i:
+                continue
+            d = (xj - xi) % R_ORDER
+            acc = acc * (xj % R_ORDER) % R_ORDER * (pow(d, -1, R_ORDER) if d else 0) % R_ORDER
+        out.append(acc)
+    return out
+
+
+def threshold_aggregate(ids, sigs):
+    """sum_i lambda_i * sig_i over affine G1 points (x, y, inf) -> affine (dkg.rs:190-206)."""
+    acc = proj_zero(FpOps)
+    for lam, s in zip(lagrange_coefficients(ids), sigs):
+        acc = proj_add(FpOps, acc, proj_mul(FpOps, affine_to_proj(FpOps, s), lam))
+    return proj_to_affine(FpOps, acc)

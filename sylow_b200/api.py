@@ -291,6 +291,34 @@ class Engine:
                  "g1_msm")
         return out, int(inf[0])
 
+    def lagrange_coefficients_batch(self, ids):
+        """ids: (n_sets, t) participant ids -> (n_sets, t, 32) Lagrange coefficients at 0 in Fr (examples/dkg.rs:216-226)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        if ids.ndim != 2:
+            raise ValueError("ids must be (n_sets, t)")
+        n_sets, t = ids.shape
+        out = np.empty((n_sets, t, 32), dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_lagrange_coefficients_batch(self._h, _ptr(ids), n_sets, t, _ptr(out)),
+                 "lagrange_coefficients_batch")
+        return out
+
+    def threshold_aggregate_batch(self, ids, sigs, sigs_inf=None):
+        """ids (n_sets, t), sigs (n_sets, t, 64) partial signatures -> (n_sets, 64) aggregated signatures + flags:
+        sum_i lambda_i * sig_i per set (examples/dkg.rs:190-206)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        if ids.ndim != 2:
+            raise ValueError("ids must be (n_sets, t)")
+        n_sets, t = ids.shape
+        sigs = np.ascontiguousarray(sigs, dtype=np.uint8)
+        if sigs.shape != (n_sets, t, 64):
+            raise ValueError("sigs must be (n_sets, t, 64)")
+        sigs_inf = None if sigs_inf is None else np.ascontiguousarray(sigs_inf, dtype=np.uint8).reshape(n_sets * t)
+        out = np.empty((n_sets, 64), dtype=np.uint8)
+        inf = np.zeros(n_sets, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_threshold_aggregate_batch(self._h, _ptr(ids), _ptr(sigs), _ptr(sigs_inf), n_sets, t,
+                                                                _ptr(out), _ptr(inf)), "threshold_aggregate_batch")
+        return out, inf
+
     # ------------------------------------------------------------------ hash / BLS
     def verify_batch_same_signer(self, pk, msgs, sigs, dst: bytes = DST) -> bool:
         pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(128)

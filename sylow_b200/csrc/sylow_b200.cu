@@ -8,6 +8,7 @@
 #include <new>
 
 #include "hash.cuh"
+#include "fr.cuh"
 #include "wire.cuh"
 
 using namespace sylow;
@@ -497,6 +498,62 @@ __global__ void k_g1_finish_sum(const uint8_t* __restrict__ in, int negate, uint
   fp_store(out, r.x);
   fp_store(out + 32, r.y);
   out_inf[0] = r.inf ? 1 : 0;
+}
+
+// ---- threshold-signature aggregation (examples/dkg.rs:190-226, threshold_signing.rs:124-155) ----
+// lambda[s][i] = prod_{j != i} x_j / (x_j - x_i) in Fr for the participant ids of set s, canonical 32-byte LE.
+__global__ void k_lagrange(const uint64_t* __restrict__ ids, size_t n_sets, size_t t, uint8_t* __restrict__ out) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_sets * t) return;
+  size_t s = g / t, i = g % t;
+  Fr lam = fr_lagrange_at_zero(ids + s * t, t, i);
+  uint32_t w[8];
+  fr_to_words(w, lam);
+  for (int k = 0; k < 8; k++) reinterpret_cast<uint32_t*>(out + g * 32)[k] = w[k];
+}
+// lambda[s][i] * sig[s][i] as a projective point in Montgomery form (96 B): no per-share inversion
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_lagrange_mul(const uint64_t* __restrict__ ids, const uint8_t* __restrict__ sigs, const uint8_t* __restrict__ sigs_inf,
+               size_t n_sets, size_t t, uint8_t* __restrict__ out) {
+  size_t g0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t g = g0 < n_sets * t ? g0 : n_sets * t - 1;  // all threads run the block-synchronised ladder
+  size_t s = g / t, i = g % t;
+  Fr lam = fr_lagrange_at_zero(ids + s * t, t, i);
+  uint32_t w[8];
+  fr_to_words(w, lam);
+  G1Aff a{fp_load(sigs + g * 64), fp_load(sigs + g * 64 + 32), sigs_inf && sigs_inf[g]};
+  G1Proj r = SY_SCALAR_MUL(affine_to_proj(a), w);
+  if (g0 != g) return;
+  fp_store_raw(out + g * 96, r.x);
+  fp_store_raw(out + g * 96 + 32, r.y);
+  fp_store_raw(out + g * 96 + 64, r.z);
+}
+// One warp per set: sum of the set's t projective points, then affine wire format + infinity flag.
+__global__ void __launch_bounds__(128) k_g1_segment_sum(const uint8_t* __restrict__ in, size_t n_sets, size_t t,
+                                                         uint8_t* __restrict__ out, uint8_t* __restrict__ out_inf) {
+  __shared__ G1Proj sh[128];
+  size_t s0 = (size_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  size_t s = s0 < n_sets ? s0 : n_sets - 1;
+  unsigned lane = threadIdx.x & 31;
+  G1Proj acc = proj_zero<Fp>();
+  for (size_t i = lane; i < t; i += 32) {
+    const uint8_t* p = in + (s * t + i) * 96;
+    acc = proj_add(acc, G1Proj{fp_load_raw(p), fp_load_raw(p + 32), fp_load_raw(p + 64)});
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (unsigned off = 16; off > 0; off >>= 1) {
+    if (lane < off) acc = proj_add(sh[threadIdx.x], sh[threadIdx.x + off]);
+    __syncthreads();
+    if (lane < off) sh[threadIdx.x] = acc;
+    __syncthreads();
+  }
+  G1Aff r = proj_to_affine(sh[threadIdx.x & ~31u]);  // every thread: the inversion ladder is block-synchronised
+  if (lane == 0 && s0 < n_sets) {
+    fp_store(out + s * 64, r.x);
+    fp_store(out + s * 64 + 32, r.y);
+    out_inf[s] = r.inf ? 1 : 0;
+  }
 }
 
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
@@ -1746,6 +1803,53 @@ int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pt
   CKS(g1_sum_reduce(ctx, ctx->scratch2.p, ctx->scratch2.p + n * 64, n, 0, ctx->out.p, ctx->out.p + 64, ctx->stream));
   CK(cudaMemcpyAsync(out, ctx->out.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(out_inf, ctx->out.p + 64, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_lagrange_coefficients_batch(sylow_b200_ctx* ctx, const uint64_t* ids, size_t n_sets, size_t t,
+                                           uint8_t* out) {
+  ENTER(ctx);
+  if ((n_sets && t) && (!ids || !out)) return SYLOW_B200_ERR_ARG;
+  size_t n = n_sets * t;
+  if (!n) return 0;
+  const uint8_t* d_ids;
+  CKS(to_dev(ctx, ctx->in_a, reinterpret_cast<const uint8_t*>(ids), n * 8, &d_ids));
+  CKS(reserve(ctx, ctx->out, n * 32));
+  k_lagrange<<<nblocks(n, 128), 128, 0, ctx->stream>>>(reinterpret_cast<const uint64_t*>(d_ids), n_sets, t, ctx->out.p);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
+int sylow_b200_threshold_aggregate_batch(sylow_b200_ctx* ctx, const uint64_t* ids, const uint8_t* sigs,
+                                         const uint8_t* sigs_inf, size_t n_sets, size_t t, uint8_t* out,
+                                         uint8_t* out_inf) {
+  ENTER(ctx);
+  if (n_sets && (!out || !out_inf || (t && (!ids || !sigs)))) return SYLOW_B200_ERR_ARG;
+  if (!n_sets) return 0;
+  if (!t) {  // the empty sum: GroupProjective::default() = infinity, encoded (0, 1) + flag
+    for (size_t s = 0; s < n_sets; s++) {
+      memset(out + s * 64, 0, 64);
+      out[s * 64 + 32] = 1;
+      out_inf[s] = 1;
+    }
+    return 0;
+  }
+  size_t n = n_sets * t;
+  const uint8_t *d_ids, *d_sigs, *d_inf;
+  CKS(to_dev(ctx, ctx->in_b, reinterpret_cast<const uint8_t*>(ids), n * 8, &d_ids));
+  CKS(to_dev(ctx, ctx->in_a, sigs, n * 64, &d_sigs));
+  CKS(to_dev(ctx, ctx->flag_a, sigs_inf, n, &d_inf));
+  CKS(reserve(ctx, ctx->scratch2, n * 96));
+  CKS(reserve(ctx, ctx->out, n_sets * 65));
+  k_lagrange_mul<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, ctx->stream>>>(
+      reinterpret_cast<const uint64_t*>(d_ids), d_sigs, d_inf, n_sets, t, ctx->scratch2.p);
+  LAUNCHED(ctx);
+  k_g1_segment_sum<<<nblocks(n_sets, 4), 128, 0, ctx->stream>>>(ctx->scratch2.p, n_sets, t, ctx->out.p,
+                                                               ctx->out.p + n_sets * 64);
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n_sets * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_inf, ctx->out.p + n_sets * 64, n_sets, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);
 }
 

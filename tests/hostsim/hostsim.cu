@@ -7,6 +7,7 @@
 // covered by the `-m gpu` parity tests.
 #include "../../sylow_b200/csrc/wire.cuh"
 #include "../../sylow_b200/csrc/hash.cuh"
+#include "../../sylow_b200/csrc/fr.cuh"
 #include <cstring>
 
 using namespace sylow;
@@ -119,6 +120,26 @@ int hs_glv_decompose(const uint8_t* k, uint8_t* out) {
   memcpy(out, k1, 16);
   memcpy(out + 16, k2, 16);
   return (n1 ? 1 : 0) | (n2 ? 2 : 0);
+}
+// Fr (fr.cuh): op 0 mul, 1 add, 2 sub, 3 inv on canonical 32-byte LE values
+void hs_fr_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  uint32_t wa[8], wb[8], w[8];
+  memcpy(wa, a, 32);
+  memcpy(wb, b, 32);
+  Fr x = fr_from_words(wa), y = fr_from_words(wb), r;
+  switch (op) {
+    case 0: r = fr_mul(x, y); break;
+    case 1: r = fr_add(x, y); break;
+    case 2: r = fr_sub(x, y); break;
+    default: r = fr_inv(x); break;
+  }
+  fr_to_words(w, r);
+  memcpy(out, w, 32);
+}
+void hs_lagrange(const uint64_t* ids, size_t t, size_t i, uint8_t* out) {
+  uint32_t w[8];
+  fr_to_words(w, fr_lagrange_at_zero(ids, t, i));
+  memcpy(out, w, 32);
 }
 int hs_g1_add(const uint8_t* p, int pinf, const uint8_t* q, int qinf, uint8_t* out) {
   G1Aff a{fp_load(p), fp_load(p + 32), pinf != 0}, b{fp_load(q), fp_load(q + 32), qinf != 0};

@@ -51,3 +51,12 @@ def test_library_targets_sm100a_with_imad_wide_carry_chains():
     fp_op = sass[sass.index("k_fp_op"):]
     fp_op = fp_op[:fp_op.index("Function :")]
     assert fp_op.count("IMAD.WIDE.U32.X") > 100
+
+
+def test_rust_bindings_are_in_sync_with_the_header():
+    """ffi/sylow-cuda-sys/src/lib.rs is generated from include/sylow_b200.h (tools/gen_rust_ffi.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_ffi.py"), "--check"])
+    assert r.returncode == 0, "run tools/gen_rust_ffi.py"

@@ -219,13 +219,15 @@ def test_scalar_mul(eng, kats):
           1 << 255, (1 << 128) - 1, 1 << 127]
     ks += [rng.randrange(o.P) for _ in range(n - len(ks) - 8)] + [rng.randrange(1 << 256) for _ in range(8)]
     out, inf = eng.g1_mul_batch(arr([w.g1_b(p) for p in ps]), arr([w.fp_b(k) for k in ks]))
-    ref = [o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k)) for p, k in zip(ps, ks)]
+    # the reference's scalars are Fp values (< p); larger 256-bit words are taken mod r (the group order)
+    red = lambda k: k if k < o.P else k % o.R_ORDER
+    ref = [o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), red(k))) for p, k in zip(ps, ks)]
     assert [w.b_g1(bytes(r), i) for r, i in zip(out, inf)] == ref
     n = 24
     qs = [w.rand_g2(rng) for _ in range(n)]
     ks = [0, 1, o.R_ORDER - 1, o.P - 1, lam, o.R_ORDER, (1 << 256) - 1] + [rng.randrange(1 << 256) for _ in range(n - 7)]
     out, inf = eng.g2_mul_batch(arr([w.g2_b(q) for q in qs]), arr([w.fp_b(k) for k in ks]))
-    ref = [o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), k)) for q, k in zip(qs, ks)]
+    ref = [o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), red(k))) for q, k in zip(qs, ks)]
     assert [w.b_g2(bytes(r), i) for r, i in zip(out, inf)] == ref
     # infinity in -> infinity out, encoded as (0, 1) + flag like GroupAffine::zero()
     out, inf = eng.g1_mul_batch(arr([w.g1_b((0, 1))]), arr([w.fp_b(7)]), pts_inf=[1])
@@ -557,3 +559,61 @@ def test_sum_msm_and_same_signer(eng):
     assert eng.verify_batch(np.repeat(pk, n, axis=0), msgs, bad) is False
     pka = w.b_g2(bytes(pk[0]))
     assert o.verify_batch([pka] * 4, msgs[:4], [w.b_g1(bytes(r)) for r in sigs[:4]]) is True
+
+
+# ------------------------------------------------------------------------------------------ threshold aggregation
+def test_lagrange_coefficients(eng):
+    """examples/dkg.rs:216-226 / threshold_signing.rs:146-155: the coefficients in Fr, per participant set."""
+    rng = random.Random(31)
+    sets = [[1, 2, 3, 4, 5], [7, 3, 9, 1, 12], [2**64 - 1, 2**63, 5, 6, 8], [10, 20, 30, 40, 50]]
+    sets += [rng.sample(range(1, 1000), 5) for _ in range(40)]
+    got = eng.lagrange_coefficients_batch(np.array(sets, dtype=np.uint64))
+    for s, row in zip(sets, got):
+        assert [int.from_bytes(bytes(x), "little") for x in row] == o.lagrange_coefficients(s)
+    # t = 1: the single coefficient is 1; a repeated id gives 0 for both copies (inv(0) = 0, fp.rs:418-424)
+    assert int.from_bytes(bytes(eng.lagrange_coefficients_batch(np.array([[9]], dtype=np.uint64))[0, 0]), "little") == 1
+    rep = eng.lagrange_coefficients_batch(np.array([[4, 4, 6]], dtype=np.uint64))[0]
+    assert [int.from_bytes(bytes(x), "little") for x in rep] == o.lagrange_coefficients([4, 4, 6])
+    t37 = rng.sample(range(1, 10**6), 37)
+    row = eng.lagrange_coefficients_batch(np.array([t37], dtype=np.uint64))[0]
+    assert [int.from_bytes(bytes(x), "little") for x in row] == o.lagrange_coefficients(t37)
+
+
+def test_threshold_aggregate(eng):
+    """sum_i lambda_i * sigma_i per set against the oracle (examples/dkg.rs:190-206), incl. t > 32 (the strided part
+    of the segment sum), an infinite share and t = 1."""
+    rng = random.Random(32)
+    for n_sets, t in ((5, 3), (2, 40), (3, 1)):
+        ids = [rng.sample(range(1, 500), t) for _ in range(n_sets)]
+        sigs = [[w.rand_g1(rng) for _ in range(t)] for _ in range(n_sets)]
+        inf = np.zeros((n_sets, t), dtype=np.uint8)
+        if t > 1:
+            inf[0, 1] = 1
+            sigs[0][1] = (0, 1, True)
+        S = np.stack([arr([w.g1_b(p) for p in row]) for row in sigs])
+        out, oinf = eng.threshold_aggregate_batch(np.array(ids, dtype=np.uint64), S, sigs_inf=inf)
+        for i in range(n_sets):
+            assert w.b_g1(bytes(out[i]), oinf[i]) == o.threshold_aggregate(ids[i], sigs[i])
+
+
+def test_threshold_signing_flow(eng):
+    """examples/threshold_signing.rs end to end: Shamir shares of a secret, partial signatures share_i * H(m), any t of n
+    aggregate (Lagrange at 0) to the signature of the group secret, which verifies under the group public key."""
+    rng = random.Random(33)
+    n, t = 7, 4
+    msg = b"threshold signing on the GPU"
+    coeffs = [rng.randrange(1, o.R_ORDER) for _ in range(t)]           # f(x), f(0) = group secret
+    share = lambda x: sum(c * pow(x, k, o.R_ORDER) for k, c in enumerate(coeffs)) % o.R_ORDER
+    ids = list(range(1, n + 1))
+    partial = eng.sign_batch(arr([w.fp_b(share(i)) for i in ids]), [msg] * n)
+    group_sig = eng.sign_batch(arr([w.fp_b(coeffs[0])]), [msg])[0]
+    pk, pk_inf = eng.g2_mul_batch(arr([w.g2_b(o.G2_GEN)]), arr([w.fp_b(coeffs[0])]))
+    subsets = [rng.sample(range(n), t) for _ in range(6)] + [list(range(t)), list(range(n - t, n))]
+    I = np.array([[ids[j] for j in sub] for sub in subsets], dtype=np.uint64)
+    S = np.stack([partial[sub] for sub in subsets])
+    agg, agg_inf = eng.threshold_aggregate_batch(I, S)
+    assert not agg_inf.any() and all(bytes(a) == bytes(group_sig) for a in agg)
+    assert eng.verify_each(np.repeat(pk, len(subsets), axis=0), [msg] * len(subsets), agg).all()
+    # t - 1 shares interpolate a different polynomial: the result is not the group signature
+    bad, _ = eng.threshold_aggregate_batch(I[:, : t - 1].copy(), S[:, : t - 1].copy())
+    assert not any(bytes(b) == bytes(group_sig) for b in bad)

@@ -27,6 +27,8 @@ def hs():
     lib.hs_hash_to_g1.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
     lib.hs_hash_to_field.argtypes = lib.hs_hash_to_g1.argtypes
     lib.hs_keccak256.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
+    lib.hs_lagrange.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p]
+    lib.hs_fr_op.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
     return lib
 
 
@@ -148,6 +150,34 @@ def test_scalar_mul_glv(hs):
         assert w.b_g2(out.raw, inf) == ref, hex(k)
     out = ctypes.create_string_buffer(64)
     assert hs.hs_g1_mul_glv(w.g1_b((0, 1)), 1, (5).to_bytes(32, "little"), out) == 1 and w.b_g1(out.raw)[:2] == (0, 1)
+
+
+def test_fr_arithmetic_and_lagrange(hs):
+    """fr.cuh against Python integers mod r; Lagrange coefficients of examples/dkg.rs:216-226."""
+    rng = random.Random(79)
+    r = o.R_ORDER
+    out = ctypes.create_string_buffer(32)
+    edge = [0, 1, 2, r - 1, r - 2, (r + 1) // 2, 2**64 - 1]
+    vals = edge + [rng.randrange(r) for _ in range(30)]
+    for a in vals:
+        for b in (vals[0], vals[3], rng.choice(vals), rng.randrange(r)):
+            for op, ref in ((0, a * b % r), (1, (a + b) % r), (2, (a - b) % r)):
+                hs.hs_fr_op(op, a.to_bytes(32, "little"), b.to_bytes(32, "little"), out)
+                assert int.from_bytes(out.raw, "little") == ref, (op, hex(a), hex(b))
+    for a in edge + [rng.randrange(r) for _ in range(4)]:
+        hs.hs_fr_op(3, a.to_bytes(32, "little"), bytes(32), out)
+        assert int.from_bytes(out.raw, "little") == (pow(a, -1, r) if a else 0)  # inv(0) = 0, fp.rs:418-424
+    # unreduced 256-bit inputs are reduced on the way in
+    hs.hs_fr_op(1, (2**256 - 1).to_bytes(32, "little"), (r + 5).to_bytes(32, "little"), out)
+    assert int.from_bytes(out.raw, "little") == (2**256 - 1 + 5) % r
+    for ids in ([1, 2, 3], [5, 2, 9, 4, 7], [2**64 - 1, 1, 2**63], [3], [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]):
+        arr = (ctypes.c_uint64 * len(ids))(*ids)
+        lam = []
+        for i in range(len(ids)):
+            hs.hs_lagrange(arr, len(ids), i, out)
+            lam.append(int.from_bytes(out.raw, "little"))
+        assert lam == o.lagrange_coefficients(ids)
+        assert sum(lam) % r == 1  # interpolating the constant polynomial 1
 
 
 def test_g1_add_eip196(hs, kats):
