@@ -736,8 +736,28 @@ SY_HD Fp fp_mul9(const Fp& a) {
   return fp_add(t, a);
 }
 
-// a^e for a fixed 256-bit exponent given as 8 LE words (uniform across the warp)
+// a^e for a fixed 256-bit exponent given as 8 LE words (uniform across the warp); top_bit = index of its
+// highest set bit.  Fixed 4-bit windows: 14 multiplications for the table, then 4 squarings and at most one
+// multiplication per window (the digit is uniform, so skipping a zero digit does not diverge).
+#ifndef SY_POW_WINDOW
+#define SY_POW_WINDOW 1
+#endif
 SY_HD_NOINLINE Fp fp_pow(const Fp& a, const uint32_t* e, int top_bit) {
+#if SY_POW_WINDOW
+  Fp tab[16];
+  tab[1] = a;
+  tab[2] = fp_sqr(a);
+  for (int i = 3; i < 16; i++) tab[i] = fp_mul(tab[i - 1], a);
+  int w = top_bit >> 2;
+  Fp r = tab[(e[w >> 3] >> ((w & 7) * 4)) & 15u];
+  for (w--; w >= 0; w--) {
+    if ((w & 3) == 3) SY_LOOP_SYNC();
+    r = fp_sqr(fp_sqr(fp_sqr(fp_sqr(r))));
+    uint32_t d = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (d) r = fp_mul(r, tab[d]);
+  }
+  return r;
+#else
   Fp r = a;
   for (int i = top_bit - 1; i >= 0; i--) {
     if ((i & 15) == 15) SY_LOOP_SYNC();
@@ -745,6 +765,7 @@ SY_HD_NOINLINE Fp fp_pow(const Fp& a, const uint32_t* e, int top_bit) {
     if ((e[i >> 5] >> (i & 31)) & 1) r = fp_mul(r, a);
   }
   return r;
+#endif
 }
 
 // p-2, (p-1)/2, (p+1)/4 as LE words
