@@ -235,13 +235,17 @@ SY_HD uint32_t fp_sgn0(const Fp& a) { return fp_from_mont(a).l[0] & 1u; }  // fp
 
 SY_HD Fp svdw_g(const Fp& x) { return fp_add(fp_mul(fp_sqr(x), x), SY_TAB(kFpThree)[0]); }  // x^3 + 3 (a = 0)
 
-// svdw.rs:180-262.  Returns false if the final sqrt check fails (MapError::SvdWError).
-SY_HD_NOINLINE bool svdw_map_to_point(const Fp& u, Fp& x, Fp& y) {
+// svdw.rs:180-262, split around its inversion so that hash_to_g1 can share ONE Fermat ladder between the two maps.
+//   svdw_head: tv1 = 1 - c1 u^2, tv2 = 1 + c1 u^2 and d = tv1 tv2 (the element the reference inverts, :195)
+//   svdw_tail: everything after tv3 = inv0(d).  Returns false if the final sqrt check fails (MapError::SvdWError).
+SY_HD void svdw_head(const Fp& u, Fp& tv1, Fp& tv2, Fp& d) {
   const Fp one = fp_one();
-  Fp tv1 = fp_mul(fp_sqr(u), SY_TAB(kSvdwC1)[0]);
-  Fp tv2 = fp_add(one, tv1);
-  tv1 = fp_sub(one, tv1);
-  Fp tv3 = fp_inv(fp_mul(tv1, tv2));
+  Fp t = fp_mul(fp_sqr(u), SY_TAB(kSvdwC1)[0]);
+  tv2 = fp_add(one, t);
+  tv1 = fp_sub(one, t);
+  d = fp_mul(tv1, tv2);
+}
+SY_HD_NOINLINE bool svdw_tail(const Fp& u, const Fp& tv1, const Fp& tv2, const Fp& tv3, Fp& x, Fp& y) {
   Fp tv4 = fp_mul(fp_mul(fp_mul(u, tv1), tv3), SY_TAB(kSvdwC3)[0]);
   Fp x1 = fp_sub(SY_TAB(kSvdwC2)[0], tv4);
   bool e1 = fp_is_square(svdw_g(x1));
@@ -258,6 +262,26 @@ SY_HD_NOINLINE bool svdw_map_to_point(const Fp& u, Fp& x, Fp& y) {
   y = fp_select(e3, y, fp_neg(y));
   return ok;
 }
+SY_HD_NOINLINE bool svdw_map_to_point(const Fp& u, Fp& x, Fp& y) {
+  Fp tv1, tv2, d;
+  svdw_head(u, tv1, tv2, d);
+  return svdw_tail(u, tv1, tv2, fp_inv(d), x, y);
+}
+// Both maps of one hash with a single inversion (Montgomery's trick): inv0(d0), inv0(d1) from inv(d0' d1') where a
+// zero d is replaced by 1 for the product and its inverse forced back to 0 (inv(0) = 0, fp.rs:418-424).
+SY_HD_NOINLINE bool svdw_map_pair(const Fp& u0, const Fp& u1, Fp& x0, Fp& y0, Fp& x1, Fp& y1) {
+  Fp a1, a2, da, b1, b2, db;
+  svdw_head(u0, a1, a2, da);
+  svdw_head(u1, b1, b2, db);
+  bool za = fp_is_zero(da), zb = fp_is_zero(db);
+  Fp ea = fp_select(za, fp_one(), da), eb = fp_select(zb, fp_one(), db);
+  Fp t = fp_inv(fp_mul(ea, eb));
+  Fp ia = fp_select(za, fp_zero(), fp_mul(t, eb));
+  Fp ib = fp_select(zb, fp_zero(), fp_mul(t, ea));
+  bool ok = svdw_tail(u0, a1, a2, ia, x0, y0);
+  ok &= svdw_tail(u1, b1, b2, ib, x1, y1);
+  return ok;
+}
 
 // g1.rs:307-331: map both field elements and add (projective result)
 SY_HD_NOINLINE bool hash_to_g1(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len,
@@ -265,8 +289,7 @@ SY_HD_NOINLINE bool hash_to_g1(const uint8_t* msg, size_t msg_len, const uint8_t
   Fp u0, u1;
   hash_to_field_xmd(hash_id, msg, msg_len, dst_prime, dst_prime_len, u0, u1);
   G1Proj a, b;
-  bool ok = svdw_map_to_point(u0, a.x, a.y);
-  ok &= svdw_map_to_point(u1, b.x, b.y);
+  bool ok = svdw_map_pair(u0, u1, a.x, a.y, b.x, b.y);
   a.z = fp_one();
   b.z = fp_one();
   out = proj_add(a, b);

@@ -141,6 +141,16 @@ void hs_lagrange(const uint64_t* ids, size_t t, size_t i, uint8_t* out) {
   fr_to_words(w, fr_lagrange_at_zero(ids, t, i));
   memcpy(out, w, 32);
 }
+// both SvdW maps of a hash through the shared inversion; out = x0 | y0 | x1 | y1
+int hs_svdw_pair(const uint8_t* u0, const uint8_t* u1, uint8_t* out) {
+  Fp x0, y0, x1, y1;
+  bool ok = svdw_map_pair(fp_load(u0), fp_load(u1), x0, y0, x1, y1);
+  fp_store(out, x0);
+  fp_store(out + 32, y0);
+  fp_store(out + 64, x1);
+  fp_store(out + 96, y1);
+  return ok ? 1 : 0;
+}
 int hs_g1_add(const uint8_t* p, int pinf, const uint8_t* q, int qinf, uint8_t* out) {
   G1Aff a{fp_load(p), fp_load(p + 32), pinf != 0}, b{fp_load(q), fp_load(q + 32), qinf != 0};
   G1Aff r = proj_to_affine(proj_add(affine_to_proj(a), affine_to_proj(b)));

@@ -180,6 +180,22 @@ def test_fr_arithmetic_and_lagrange(hs):
         assert sum(lam) % r == 1  # interpolating the constant polynomial 1
 
 
+def test_svdw_pair_shared_inversion(hs):
+    """The two SvdW maps of one hash share a single inversion; inv0 semantics (u = 1/2 makes tv1 * tv2 = 0,
+    svdw.rs:195 + fp.rs:418-424) must survive the sharing on either side and on both."""
+    rng = random.Random(80)
+    half = (o.P + 1) // 2
+    out = ctypes.create_string_buffer(128)
+    specials = [0, 1, half, o.P - half, o.P - 1]
+    pairs = [(a, b) for a in specials for b in specials] + [(rng.randrange(o.P), rng.randrange(o.P)) for _ in range(6)]
+    pairs += [(half, rng.randrange(o.P)), (rng.randrange(o.P), half)]
+    for u0, u1 in pairs:
+        assert hs.hs_svdw_pair(w.fp_b(u0), w.fp_b(u1), out) == 1
+        got = [int.from_bytes(out.raw[32 * i: 32 * i + 32], "little") for i in range(4)]
+        assert tuple(got[:2]) == tuple(o.svdw_map_to_point(u0)[:2]), hex(u0)
+        assert tuple(got[2:]) == tuple(o.svdw_map_to_point(u1)[:2]), hex(u1)
+
+
 def test_g1_add_eip196(hs, kats):
     inp = bytes.fromhex(kats["eip196_add"]["input"])
     c = [int.from_bytes(inp[32 * i: 32 * i + 32], "big") for i in range(4)]
