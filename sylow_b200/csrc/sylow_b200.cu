@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "hash.cuh"
 #include "fr.cuh"
@@ -816,6 +817,9 @@ struct DevBuf {
 struct sylow_b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host<->device copies of the chunked host-pointer calls
+  cudaStream_t stream2 = nullptr;                      // second compute stream: odd chunks (their tails overlap)
+  int sms = 148;
   int last_cuda = 0;
   uint64_t launches = 0;
   DevBuf in_a, in_b, in_c, in_d, flag_a, flag_b, out, scratch0, scratch1, scratch2;
@@ -875,6 +879,10 @@ int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
   ctx->device = device_id;
   cudaError_t e = cudaSetDevice(device_id);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device_id);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fail, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_fail, 0, sizeof(int));
   if (e != cudaSuccess) {
@@ -898,6 +906,9 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->sum0.p) cudaFree(ctx->sum0.p);
   if (ctx->sum1.p) cudaFree(ctx->sum1.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
   return 0;
 }
@@ -1222,20 +1233,76 @@ static int finish(sylow_b200_ctx* ctx) {
   if (!(ctx)) return SYLOW_B200_ERR_ARG;          \
   CK(cudaSetDevice((ctx)->device));
 
+// Host-pointer pairing / Miller-loop batch.  Large batches are cut into chunks of four full waves (SMs x 256 threads
+// x 4) and pipelined over three streams: the host->device copy of chunk c+1 and the device->host copy of chunk c-1
+// run under the kernels of chunk c, so the PCIe time of the 576 bytes per pairing disappears from the call.
+static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                        const uint8_t* g2_inf, size_t n, uint8_t* out, bool final_exp) {
+  const uint8_t *d1i, *d2i;
+  CKS(reserve(ctx, ctx->in_a, n * 64));
+  CKS(reserve(ctx, ctx->in_b, n * 128));
+  CKS(reserve(ctx, ctx->out, n * 384));
+  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
+  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
+  if (d1i || d2i) CK(cudaStreamSynchronize(ctx->stream));  // the flags are read from both compute streams
+  const size_t chunk = (size_t)ctx->sms * SY_MILLER_THREADS * 4;
+  const size_t n_chunks = n <= 2 * chunk ? 1 : (n + chunk - 1) / chunk;
+  const size_t step = n_chunks == 1 ? n : chunk;
+  std::vector<cudaEvent_t> ev(2 * n_chunks, nullptr);
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; i < ev.size() && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  auto d2h = [&](size_t c) {
+    size_t off = c * step, m = off + step < n ? step : n - off;
+    cudaError_t r = cudaStreamWaitEvent(ctx->copy_out, ev[2 * c + 1], 0);
+    if (r == cudaSuccess)
+      r = cudaMemcpyAsync(out + off * 384, ctx->out.p + off * 384, m * 384, cudaMemcpyDeviceToHost, ctx->copy_out);
+    return r;
+  };
+  for (size_t c = 0; c < n_chunks && e == cudaSuccess && rc == 0; c++) {
+    size_t off = c * step, m = off + step < n ? step : n - off;
+    e = cudaMemcpyAsync(ctx->in_a.p + off * 64, g1 + off * 64, m * 64, cudaMemcpyHostToDevice, ctx->copy_in);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->in_b.p + off * 128, g2 + off * 128, m * 128, cudaMemcpyHostToDevice, ctx->copy_in);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[2 * c], ctx->copy_in);
+    cudaStream_t cs = (c & 1) ? ctx->stream2 : ctx->stream;
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev[2 * c], 0);
+    if (e != cudaSuccess) break;
+    const uint8_t* f1 = d1i ? d1i + off : nullptr;
+    const uint8_t* f2 = d2i ? d2i + off : nullptr;
+    uint8_t* o = ctx->out.p + off * 384;
+    if (final_exp)
+      rc = sylow_b200_pairing_batch_dev(ctx, ctx->in_a.p + off * 64, f1, ctx->in_b.p + off * 128, f2, m, o, cs);
+    else
+      rc = sylow_b200_miller_loop_batch_dev(ctx, ctx->in_a.p + off * 64, f1, ctx->in_b.p + off * 128, f2, m, o, cs);
+    if (rc) break;
+    e = cudaEventRecord(ev[2 * c + 1], cs);
+    // the device->host copy of the PREVIOUS chunk is issued after this chunk's kernels are queued: with pageable
+    // host memory that copy blocks the calling thread, and the GPU then still has a chunk of work in front of it
+    if (e == cudaSuccess && c > 0) e = d2h(c - 1);
+  }
+  if (e == cudaSuccess && rc == 0) e = d2h(n_chunks - 1);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->copy_out);
+  cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e4 = cudaStreamSynchronize(ctx->copy_in);
+  cudaError_t e5 = cudaStreamSynchronize(ctx->stream2);
+  for (cudaEvent_t v : ev)
+    if (v) cudaEventDestroy(v);
+  if (rc) return rc;
+  if (e == cudaSuccess) e = e2;
+  if (e == cudaSuccess) e = e3;
+  if (e == cudaSuccess) e = e4;
+  if (e == cudaSuccess) e = e5;
+  if (e != cudaSuccess) return fail_cuda(ctx, e);
+  return 0;
+}
+
 int sylow_b200_pairing_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                              const uint8_t* g2_inf, size_t n, uint8_t* gt_out) {
   ENTER(ctx);
   if (n && (!g1 || !g2 || !gt_out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
-  const uint8_t *d1, *d1i, *d2, *d2i;
-  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
-  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
-  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
-  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
-  CKS(reserve(ctx, ctx->out, n * 384));
-  CKS(sylow_b200_pairing_batch_dev(ctx, d1, d1i, d2, d2i, n, ctx->out.p, nullptr));
-  CK(cudaMemcpyAsync(gt_out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
-  return finish(ctx);
+  return pairing_host(ctx, g1, g1_inf, g2, g2_inf, n, gt_out, true);
 }
 
 int sylow_b200_miller_loop_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
@@ -1243,15 +1310,7 @@ int sylow_b200_miller_loop_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const u
   ENTER(ctx);
   if (n && (!g1 || !g2 || !f_out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
-  const uint8_t *d1, *d1i, *d2, *d2i;
-  CKS(to_dev(ctx, ctx->in_a, g1, n * 64, &d1));
-  CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
-  CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
-  CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
-  CKS(reserve(ctx, ctx->out, n * 384));
-  CKS(sylow_b200_miller_loop_batch_dev(ctx, d1, d1i, d2, d2i, n, ctx->out.p, nullptr));
-  CK(cudaMemcpyAsync(f_out, ctx->out.p, n * 384, cudaMemcpyDeviceToHost, ctx->stream));
-  return finish(ctx);
+  return pairing_host(ctx, g1, g1_inf, g2, g2_inf, n, f_out, false);
 }
 
 int sylow_b200_miller_product(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,

@@ -4,6 +4,7 @@ checksum of checksums - bilinearity turns the product of all outputs into one ex
 Gt::generator() that the oracle can check:  prod_i e(a_i G1, b_i G2) = GT^(sum a_i b_i mod r)."""
 import numpy as np
 import pytest
+import torch
 
 from oracle import bn254_py as o
 from oracle import c_oracle as c
@@ -55,16 +56,28 @@ def test_pairing_batch_2pow20(eng):
     P, pinf = eng.g1_mul_batch(g1, a)
     Q, qinf = eng.g2_mul_batch(g2, b)
     assert not pinf.any() and not qinf.any()
-    gt = eng.pairing_batch(P, Q)
+    # a few infinite inputs on both sides of the host path's chunk boundaries (4 waves = SMs * 1024 pairs per chunk):
+    # pairing(inf, .) = pairing(., inf) = identity (pairing.rs:876-886)
+    chunk = torch.cuda.get_device_properties(0).multi_processor_count * 1024
+    holes = [chunk - 1, chunk, 3 * chunk + 5, n - 1]
+    pinf[holes[:2]] = 1
+    qinf[holes[2:]] = 1
+    gt = eng.pairing_batch(P, Q, g1_inf=pinf, g2_inf=qinf)
+    one = np.frombuffer(w.fp12_b(o.FP12_ONE), dtype=np.uint8)
+    assert all((gt[h] == one).all() for h in holes)
+    a, b = a.copy(), b.copy()
+    a[holes] = 0  # they drop out of the checksum below
     # (1) prefix and a scattered sample, bit-exact against the CPU oracle
     idx = np.concatenate([np.arange(512), rs.randint(0, n, size=512)])
+    idx = idx[~np.isin(idx, holes)]
     assert (gt[idx] == c.pairing_batch(P[idx], Q[idx])).all()
     assert (P[idx] == c.g1_mul_batch(g1[idx], a[idx])[0]).all() and (Q[idx] == c.g2_mul_batch(g2[idx], b[idx])[0]).all()
     # (2) checksum of checksums over all 2^20 outputs
     e = sum(x * y for x, y in zip(_ints(a), _ints(b))) % R
     assert (eng.fp12_product(gt) == _gt_pow_gen(eng, e)).all()
     # the same identity through the Miller-product path (glued_miller_loop + one final exponentiation)
-    assert (eng.final_exp_batch(eng.miller_product(P, Q).reshape(1, 384))[0] == _gt_pow_gen(eng, e)).all()
+    assert (eng.final_exp_batch(eng.miller_product(P, Q, g1_inf=pinf, g2_inf=qinf).reshape(1, 384))[0]
+            == _gt_pow_gen(eng, e)).all()
     # oracle cross-check of the right-hand side
     assert w.b_fp12(bytes(_gt_pow_gen(eng, e))) == o.gt_mul(o.pairing_affine(o.G1_GEN, o.G2_GEN), e)
 
