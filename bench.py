@@ -363,6 +363,16 @@ def main():
         extras["g2_scalar_muls_per_s"] = world * nm / (max_over_ranks(ms_2) * 1e-3)
         extras["scalar_muls_per_gpu"] = nm
         del d_k, d_p1, d_p2, d_o1, d_o2
+        # threshold aggregation, 2^15 sets of 8 partial signatures (host buffers, wall clock)
+        tt = 8
+        ns = max(1, min(1 << 15, n // tt))
+        ids = np.tile(np.arange(1, tt + 1, dtype=np.uint64), (ns, 1)) + (np.arange(ns, dtype=np.uint64) % 5)[:, None]
+        h_sig = d_g1[: ns * tt].cpu().numpy().reshape(ns, tt, 64)
+        eng.threshold_aggregate_batch(ids, h_sig)
+        t0 = time.perf_counter()
+        eng.threshold_aggregate_batch(ids, h_sig)
+        extras["threshold_aggregations_per_s"] = world * ns / max_over_ranks(time.perf_counter() - t0)
+        extras["threshold_shares_per_set"] = tt
 
     cpu = None
     if rank == 0 and world == 1:

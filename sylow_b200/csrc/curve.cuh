@@ -4,7 +4,7 @@
 // Value-level replacement of /root/reference/src/groups/group.rs:339-386 (double), :528-599 (add),
 // :639-667 (scalar multiplication by an Fp-range scalar) and :475-495 (projective -> affine).  Parity
 // is defined on AFFINE coordinates, so the scalar multiplication is free to use a
-// fixed 4-bit window ladder with no data-dependent branches instead of the reference's NAF loop.
+// GLV split with fixed 4-bit windows and no data-dependent branches instead of the reference's NAF loop.
 #pragma once
 #include "constants.cuh"
 
