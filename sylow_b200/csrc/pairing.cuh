@@ -248,23 +248,29 @@ SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
   Fp12 f = fp12_mul(fp12_conj(f0), fp12_inv(f0));
   SY_LOOP_SYNC();
   Fp12 inp = fp12_mul(fp12_frobenius(f, 2), f);
-  // hard part (:437-489)
-  Fp12 a = exp_by_neg_z(inp);
-  Fp12 b = cyclotomic_squared(a);
-  Fp12 c = cyclotomic_squared(b);
-  Fp12 d = fp12_mul(c, b);
-  Fp12 e = exp_by_neg_z(d);
-  Fp12 g = exp_by_neg_z(cyclotomic_squared(e));
+  // hard part (:437-489); the names follow the reference, dead values give their frame slot to later ones
+  Fp12 b, d, e, k, l;
+  {
+    Fp12 a = exp_by_neg_z(inp);
+    b = cyclotomic_squared(a);
+    a = cyclotomic_squared(b);  // c
+    d = fp12_mul(a, b);
+    e = exp_by_neg_z(d);
+    a = cyclotomic_squared(e);
+    Fp12 g = exp_by_neg_z(a);
+    SY_LOOP_SYNC();
+    a = fp12_mul(fp12_conj(g), e);
+    k = fp12_mul(a, fp12_conj(d));
+  }
+  l = fp12_mul(k, b);
   SY_LOOP_SYNC();
-  Fp12 k = fp12_mul(fp12_mul(fp12_conj(g), e), fp12_conj(d));
-  Fp12 l = fp12_mul(k, b);
+  b = fp12_mul(k, e);
+  d = fp12_mul(inp, b);                 // n
+  e = fp12_mul(fp12_frobenius(l, 1), d);  // p
   SY_LOOP_SYNC();
-  Fp12 n = fp12_mul(inp, fp12_mul(k, e));
-  Fp12 p = fp12_mul(fp12_frobenius(l, 1), n);
-  SY_LOOP_SYNC();
-  Fp12 r = fp12_mul(fp12_frobenius(k, 2), p);
-  Fp12 u = fp12_frobenius(fp12_mul(fp12_conj(inp), l), 3);
-  return fp12_mul(u, r);
+  b = fp12_mul(fp12_frobenius(k, 2), e);  // r
+  d = fp12_mul(fp12_conj(inp), l);
+  return fp12_mul(fp12_frobenius(d, 3), b);
 }
 
 
