@@ -49,6 +49,7 @@ typedef enum {
 
 #define SYLOW_B200_HASH_KECCAK256 0   /* XMDExpander::<Keccak256>, lib.rs:181,225 */
 #define SYLOW_B200_HASH_SHA256 1      /* XMDExpander::<Sha256>, the digest of the reference's RFC 9380 vectors */
+#define SYLOW_B200_HASH_SHAKE128 2    /* XOFExpander::<Shake128> (hasher.rs:258-330), security parameter k = 128 */
 
 /* Context: owns one stream and growable device/pinned staging buffers on `device_id`. */
 int sylow_b200_create(sylow_b200_ctx** out, int device_id);

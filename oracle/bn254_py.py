@@ -792,10 +792,24 @@ def expand_message_xmd(msg: bytes, dst: bytes, len_in_bytes: int, hash_id: str =
     return b"".join(bvals)[:len_in_bytes]
 
 
+def expand_message_xof(msg: bytes, dst: bytes, len_in_bytes: int, security_param: int = SECURITY_BITS) -> bytes:
+    """XOFExpander::<Shake128>::new + expand_message, src/hasher.rs:274-290,312-329."""
+    if len(dst) > 255:
+        dst = hashlib.shake_128(b"H2C-OVERSIZE-DST-" + dst).digest((2 * security_param + 7) // 8)
+    dst_prime = dst + bytes([len(dst)])
+    return hashlib.shake_128(msg + len_in_bytes.to_bytes(2, "big") + dst_prime).digest(len_in_bytes)
+
+
+def expand_message(msg: bytes, dst: bytes, len_in_bytes: int, hash_id: str = "keccak256") -> bytes:
+    if hash_id == "shake128":
+        return expand_message_xof(msg, dst, len_in_bytes)
+    return expand_message_xmd(msg, dst, len_in_bytes, hash_id)
+
+
 def hash_to_field(msg: bytes, dst: bytes = DST, count: int = 2, size: int = 48,
                   hash_id: str = "keccak256"):
     """Expander::hash_to_field, src/hasher.rs:84-128 (always two outputs, Q11)."""
-    exp = expand_message_xmd(msg, dst, count * size, hash_id)
+    exp = expand_message(msg, dst, count * size, hash_id)
     return [int.from_bytes(exp[size * i: size * (i + 1)], "big") % P for i in range(2)]
 
 

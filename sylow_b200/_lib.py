@@ -14,6 +14,7 @@ OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOT_ON_CURVE, ERR_NOT_IN_SUBGROUP, ERR_CANNOT_HASH, ERR_DECODE, ERR_NOMEM = range(-1, -8, -1)
 HASH_KECCAK256 = 0
 HASH_SHA256 = 1
+HASH_SHAKE128 = 2
 
 # every symbol include/sylow_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 _P = c_void_p

@@ -194,6 +194,60 @@ SY_HD_NOINLINE void expand_message_xmd(const uint8_t* msg, size_t msg_len, const
   }
 }
 
+// ---- SHAKE128 (FIPS 202: rate 168 bytes, domain bits 1111 -> pad byte 0x1f), the XOF of XOFExpander::<Shake128>
+// (hasher.rs:258-330 and its RFC 9380 vectors :345-428)
+struct Shake128 {
+  uint64_t s[25];
+  int pos;
+};
+SY_HD void shake_init(Shake128& k) {
+  for (int i = 0; i < 25; i++) k.s[i] = 0;
+  k.pos = 0;
+}
+SY_HD void shake_absorb_byte(Shake128& k, uint8_t b) {
+  k.s[k.pos >> 3] ^= (uint64_t)b << ((k.pos & 7) * 8);
+  if (++k.pos == 168) {
+    keccak_f1600(k.s);
+    k.pos = 0;
+  }
+}
+// pad, switch to squeezing and write n output bytes
+SY_HD void shake_squeeze(Shake128& k, uint8_t* out, size_t n) {
+  k.s[k.pos >> 3] ^= (uint64_t)0x1f << ((k.pos & 7) * 8);
+  k.s[20] ^= 0x8000000000000000ull;  // byte 167
+  keccak_f1600(k.s);
+  int pos = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (pos == 168) {
+      keccak_f1600(k.s);
+      pos = 0;
+    }
+    out[i] = (uint8_t)(k.s[pos >> 3] >> ((pos & 7) * 8));
+    pos++;
+  }
+}
+// XOFExpander::expand_message (hasher.rs:312-329): H(msg || I2OSP(len, 2) || DST' || I2OSP(len(DST'), 1), len)
+SY_HD_NOINLINE void expand_message_xof(const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len,
+                                       uint32_t len_in_bytes, uint8_t* out) {
+  Shake128 k;
+  shake_init(k);
+  for (size_t i = 0; i < msg_len; i++) shake_absorb_byte(k, msg[i]);
+  shake_absorb_byte(k, (uint8_t)(len_in_bytes >> 8));
+  shake_absorb_byte(k, (uint8_t)len_in_bytes);
+  for (size_t i = 0; i < dst_prime_len; i++) shake_absorb_byte(k, dst_prime[i]);
+  shake_squeeze(k, out, len_in_bytes);
+}
+// the expander selected by hash_id: 0 XMD-Keccak-256 (sylow's sign/verify), 1 XMD-SHA-256, 2 XOF-SHAKE128
+SY_HD void expand_message(int hash_id, const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime, size_t dst_prime_len,
+                          uint32_t len_in_bytes, uint8_t* out) {
+  if (hash_id == 2)
+    expand_message_xof(msg, msg_len, dst_prime, dst_prime_len, len_in_bytes, out);
+  else if (hash_id == 1)
+    expand_message_xmd<Sha256>(msg, msg_len, dst_prime, dst_prime_len, len_in_bytes, out);
+  else
+    expand_message_xmd<Keccak256H>(msg, msg_len, dst_prime, dst_prime_len, len_in_bytes, out);
+}
+
 // 48 big-endian bytes -> value mod p, in Montgomery form (hasher.rs:93-111)
 SY_HD Fp fp_from_be48_mod(const uint8_t* b) {
   Fp hi = fp_zero(), lo;
@@ -211,14 +265,11 @@ SY_HD Fp fp_from_be48_mod(const uint8_t* b) {
 }
 
 // hash_to_field(msg, count = 2, L = 48) (hasher.rs:84-128): expand to 96 bytes, two 48-byte big-endian values mod p.
-// hash_id: 0 = Keccak-256 (sylow's sign/verify), 1 = SHA-256.
+// hash_id: 0 = XMD Keccak-256 (sylow's sign/verify), 1 = XMD SHA-256, 2 = XOF SHAKE128.
 SY_HD_NOINLINE void hash_to_field_xmd(int hash_id, const uint8_t* msg, size_t msg_len, const uint8_t* dst_prime,
                                       size_t dst_prime_len, Fp& u0, Fp& u1) {
   uint8_t uni[96];
-  if (hash_id == 1)
-    expand_message_xmd<Sha256>(msg, msg_len, dst_prime, dst_prime_len, 96, uni);
-  else
-    expand_message_xmd<Keccak256H>(msg, msg_len, dst_prime, dst_prime_len, 96, uni);
+  expand_message(hash_id, msg, msg_len, dst_prime, dst_prime_len, 96, uni);
   u0 = fp_from_be48_mod(uni);
   u1 = fp_from_be48_mod(uni + 48);
 }

@@ -49,7 +49,7 @@ using namespace sylow;
 struct DstPrime {
   uint8_t b[256];
   uint32_t len;
-  int hash_id;  // 0 Keccak-256, 1 SHA-256
+  int hash_id;  // 0 XMD Keccak-256, 1 XMD SHA-256, 2 XOF SHAKE128
 };
 
 // f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
@@ -430,10 +430,7 @@ __global__ void k_expand_message(const uint8_t* __restrict__ msgs, const uint64_
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t o0 = offsets[i], o1 = offsets[i + 1];
-  if (dst.hash_id == 1)
-    expand_message_xmd<Sha256>(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, len_in_bytes, out + i * len_in_bytes);
-  else
-    expand_message_xmd<Keccak256H>(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, len_in_bytes, out + i * len_in_bytes);
+  expand_message(dst.hash_id, msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, len_in_bytes, out + i * len_in_bytes);
 }
 // out[i] = hash_to_field(msg_i, 2, 48): two canonical Fp (Expander::hash_to_field, hasher.rs:84-128)
 __global__ void k_hash_to_field(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
@@ -450,7 +447,13 @@ __global__ void k_hash_to_field(const uint8_t* __restrict__ msgs, const uint64_t
 __global__ void k_oversize_dst(const uint8_t* __restrict__ dst, size_t dst_len, int hash_id, uint8_t* __restrict__ out32) {
   if (blockIdx.x || threadIdx.x) return;
   const char prefix[] = "H2C-OVERSIZE-DST-";
-  if (hash_id == 1) {
+  if (hash_id == 2) {  // XOFExpander::new (hasher.rs:274-281): ceil(2k / 8) = 32 output bytes for k = 128
+    Shake128 h;
+    shake_init(h);
+    for (int i = 0; i < 17; i++) shake_absorb_byte(h, (uint8_t)prefix[i]);
+    for (size_t i = 0; i < dst_len; i++) shake_absorb_byte(h, dst[i]);
+    shake_squeeze(h, out32, 32);
+  } else if (hash_id == 1) {
     Sha256 h;
     hash_init(h);
     for (int i = 0; i < 17; i++) hash_absorb_byte(h, (uint8_t)prefix[i]);
@@ -1042,7 +1045,8 @@ int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const u
 }
 
 static int make_dst_prime(sylow_b200_ctx* ctx, const uint8_t* dst, size_t dst_len, int hash_id, DstPrime& dp) {
-  if (hash_id != SYLOW_B200_HASH_KECCAK256 && hash_id != SYLOW_B200_HASH_SHA256) return SYLOW_B200_ERR_ARG;
+  if (hash_id != SYLOW_B200_HASH_KECCAK256 && hash_id != SYLOW_B200_HASH_SHA256 && hash_id != SYLOW_B200_HASH_SHAKE128)
+    return SYLOW_B200_ERR_ARG;
   if (dst_len && !dst) return SYLOW_B200_ERR_ARG;
   memset(dp.b, 0, sizeof(dp.b));
   dp.hash_id = hash_id;
@@ -1795,8 +1799,9 @@ int sylow_b200_expand_message_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, co
   ENTER(ctx);
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
-  // ell = ceil(len / 32) <= 255 and len < 2^16 (hasher.rs:211-216, i2osp(len, 2))
-  if (len_in_bytes == 0 || (len_in_bytes + 31) / 32 > 255 || len_in_bytes > 65535) return SYLOW_B200_ERR_ARG;
+  // XMD: ell = ceil(len / 32) <= 255; both: len < 2^16 (hasher.rs:211-216, i2osp(len, 2))
+  if (len_in_bytes == 0 || len_in_bytes > 65535) return SYLOW_B200_ERR_ARG;
+  if (hash_id != SYLOW_B200_HASH_SHAKE128 && (len_in_bytes + 31) / 32 > 255) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
   if (!out) return SYLOW_B200_ERR_ARG;
   const uint8_t* dm;

@@ -299,6 +299,16 @@ class XMDExpander:
         return [Fp(int.from_bytes(row[:32], "little")), Fp(int.from_bytes(row[32:], "little"))]
 
 
+class XOFExpander(XMDExpander):
+    """XOFExpander::<Shake128>::new(dst, 128) (hasher.rs:258-330)."""
+
+    def __init__(self, dst: bytes = DST, security_param: int = SECURITY_BITS):
+        if security_param != SECURITY_BITS:
+            raise ValueError("only k = 128 is supported")
+        self.dst = bytes(dst)
+        self.hash_id = _lib.HASH_SHAKE128
+
+
 @dataclass(frozen=True)
 class KeyPair:
     """lib.rs:105-137"""

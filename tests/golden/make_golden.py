@@ -171,6 +171,17 @@ def main():
                                 "vectors": xmd_map(378, 389)}
     assert len(k["xmd_sha256_short"]["vectors"]) == 3 and len(k["xmd_sha256_long_dst"]["vectors"]) == 3
 
+    # --- RFC 9380 expand_message_xof SHAKE128 vectors (src/hasher.rs:345-366, 393-428)
+    xof_map = xmd_map
+
+    xof_dst_long = re.search(r'let dst = b"([^"]+)"', lines("src/hasher.rs", 413, 418)).group(1)
+    k["xof_shake128_short"] = {"source": "src/hasher.rs:345-355,394-398", "dst": "QUUX-V01-CS02-with-expander-SHAKE128",
+                               "len_in_bytes": 32, "vectors": xof_map(345, 356)}
+    k["xof_shake128_long_dst"] = {"source": "src/hasher.rs:357-366,413-417", "dst": xof_dst_long, "len_in_bytes": 32,
+                                  "vectors": xof_map(357, 367)}
+    assert len(k["xof_shake128_short"]["vectors"]) == 3 and len(k["xof_shake128_long_dst"]["vectors"]) == 3
+    assert len(xof_dst_long) > 255
+
     with open(OUT, "w") as f:
         json.dump(k, f, indent=1, sort_keys=True)
     print("wrote", OUT, "with", len(k), "entries")

@@ -168,10 +168,7 @@ void hs_gt_pow(const uint8_t* g, const uint8_t* k, uint8_t* out) {
 }
 
 void hs_expand(int hash_id, const uint8_t* msg, size_t n, const uint8_t* dst_prime, size_t dn, uint32_t len, uint8_t* out) {
-  if (hash_id == 1)
-    expand_message_xmd<Sha256>(msg, n, dst_prime, dn, len, out);
-  else
-    expand_message_xmd<Keccak256H>(msg, n, dst_prime, dn, len, out);
+  expand_message(hash_id, msg, n, dst_prime, dn, len, out);
 }
 
 void hs_keccak256(const uint8_t* msg, size_t n, uint8_t* out32) {

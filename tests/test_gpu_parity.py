@@ -511,13 +511,18 @@ def test_expander_rfc9380_vectors(eng, kats):
         msgs = [m.encode() for m, _ in t["vectors"]]
         out = eng.expand_message_batch(msgs, t["dst"].encode(), t["len_in_bytes"], hash_id=_lib.HASH_SHA256)
         assert [bytes(r).hex() for r in out] == [e for _, e in t["vectors"]]
+    for name in ("xof_shake128_short", "xof_shake128_long_dst"):  # XOFExpander::<Shake128>, hasher.rs:393-428
+        t = kats[name]
+        msgs = [m.encode() for m, _ in t["vectors"]]
+        out = eng.expand_message_batch(msgs, t["dst"].encode(), t["len_in_bytes"], hash_id=_lib.HASH_SHAKE128)
+        assert [bytes(r).hex() for r in out] == [e for _, e in t["vectors"]]
     rng = random.Random(26)
     msgs = [b"", b"abc", bytes(rng.randrange(256) for _ in range(300))]
-    for hid, name in ((_lib.HASH_KECCAK256, "keccak256"), (_lib.HASH_SHA256, "sha256")):
+    for hid, name in ((_lib.HASH_KECCAK256, "keccak256"), (_lib.HASH_SHA256, "sha256"), (_lib.HASH_SHAKE128, "shake128")):
         for dst in (o.DST, b"Q" * 256, b""):
             for ln in (32, 96, 200):
                 out = eng.expand_message_batch(msgs, dst, ln, hash_id=hid)
-                assert [bytes(r) for r in out] == [o.expand_message_xmd(m, dst, ln, name) for m in msgs]
+                assert [bytes(r) for r in out] == [o.expand_message(m, dst, ln, name) for m in msgs]
             f = eng.hash_to_field_batch(msgs, dst, hash_id=hid)
             assert [[w.b_fp(bytes(r[:32])), w.b_fp(bytes(r[32:]))] for r in f] == [o.hash_to_field(m, dst, 2, 48, name) for m in msgs]
             pts, _ = eng.hash_to_g1_batch(msgs, dst, hash_id=hid)

@@ -134,3 +134,11 @@ def test_expander(s, kats):
     for m, exp in t["vectors"]:
         assert e.expand_message(m.encode(), 32).hex() == exp
         assert len(e.hash_to_field(m.encode(), 2, 48)) == 2
+    for name in ("xof_shake128_short", "xof_shake128_long_dst"):  # src/hasher.rs:393-428
+        t = kats[name]
+        x = s.XOFExpander(t["dst"].encode(), 128)
+        for m, exp in t["vectors"]:
+            assert x.expand_message(m.encode(), 32).hex() == exp
+    # any Expander drives hash_to_curve (GroupTrait::hash_to_curve<E: Expander>, group.rs:137)
+    p = s.G1Projective.hash_to_curve(s.XOFExpander(DST, 128), MSG)
+    assert (int(p.x), int(p.y)) == o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(MSG, DST, "shake128"))[:2]

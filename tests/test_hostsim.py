@@ -293,9 +293,15 @@ def test_expander_generic(hs, kats):
         out = ctypes.create_string_buffer(32)
         hs.hs_expand(1, m.encode(), len(m), dp, len(dp), 32, out)
         assert out.raw.hex() == e
+    t = kats["xof_shake128_short"]  # XOFExpander::<Shake128>, hasher.rs:345-355,394-410
+    dp = t["dst"].encode() + bytes([len(t["dst"])])
+    for m, e in t["vectors"]:
+        out = ctypes.create_string_buffer(32)
+        hs.hs_expand(2, m.encode(), len(m), dp, len(dp), 32, out)
+        assert out.raw.hex() == e
     dp = o.DST + bytes([len(o.DST)])
-    for hid, name in ((0, "keccak256"), (1, "sha256")):
-        for ln in (32, 96, 177):
+    for hid, name in ((0, "keccak256"), (1, "sha256"), (2, "shake128")):
+        for ln in (32, 96, 177, 400):  # 400 > the 168-byte SHAKE128 rate: several squeeze permutations
             out = ctypes.create_string_buffer(ln)
             hs.hs_expand(hid, b"abcdef" * 30, 180, dp, len(dp), ln, out)
-            assert out.raw == o.expand_message_xmd(b"abcdef" * 30, o.DST, ln, name)
+            assert out.raw == o.expand_message(b"abcdef" * 30, o.DST, ln, name)

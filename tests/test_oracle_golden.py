@@ -124,6 +124,14 @@ def test_xmd_sha256(kats):
             assert o.expand_message_xmd(msg.encode(), t["dst"].encode(), t["len_in_bytes"], "sha256").hex() == exp
 
 
+def test_xof_shake128(kats):
+    """src/hasher.rs:393-428: XOFExpander::<Shake128>, short and oversize DST."""
+    for name in ("xof_shake128_short", "xof_shake128_long_dst"):
+        t = kats[name]
+        for msg, exp in t["vectors"]:
+            assert o.expand_message_xof(msg.encode(), t["dst"].encode(), t["len_in_bytes"]).hex() == exp
+
+
 def test_keccak256_kat():
     # public Keccak-256 KATs (legacy padding, not SHA3-256)
     assert o.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
