@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(256, 1) k_tower_probe(int iters, const uint32_
 //   MODE 2: MODE 1 with the odd warps skewed by one addition phase
 //   MODE 3: MODE 1 with the odd warps skewed by half a multiplication
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) k_overlap_probe(int iters, const uint32_t* src, uint32_t* sink) {
+__global__ void __launch_bounds__(1024, 1) k_overlap_probe(int iters, const uint32_t* src, uint32_t* sink) {
   Fp x = fp_one(), y, u, v;
   for (int i = 0; i < 8; i++) {
     y.l[i] = src[i] & (i == 7 ? 0x1FFFFFFFu : 0xFFFFFFFFu);

@@ -15,9 +15,11 @@ names = {0: "fp_mul only", 39: "fp_sub + fp_add only (per pair)", 40: "mul + 8 i
          41: "mul -> 8 adds -> mul (serial phases)", 42: "serial phases, odd warps skewed by an add phase",
          43: "serial phases, odd warps skewed by ~half a mul"}
 res = []
-for threads, bps in ((128, 1), (256, 1), (384, 1), (512, 1)):
+for threads, bps in ((128, 1), (256, 1), (384, 1), (512, 1), (768, 1), (1024, 1)):
     for variant in (0, 39, 40, 41, 42, 43):
         best = 1e30
+        if variant == 39 and threads > 256:  # k_tower_probe is bounded to the pairing kernels' 256 threads
+            continue
         for _ in range(3):
             ms, ops = eng.imad_probe(variant, sms * bps, threads, 4000)
             best = min(best, ms)
