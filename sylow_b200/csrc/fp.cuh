@@ -10,6 +10,10 @@
 // IMAD.WIDE.U32(.X) with a predicate carry, so one Fp multiplication is 136 IMAD-pipe instructions
 // (64 for a*b, 64 for m*p, 8 for m) - the 136 "limb products" SURVEY.md 8(d) counts.
 #pragma once
+#if defined(SYLOW_HOSTSIM)
+#include <cstdio>
+#include <cstdlib>
+#endif
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -719,6 +723,131 @@ inline void fp_add_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   }
 }
 #endif
+
+// ---- lazy reduction above Fp2 (tower.cuh fp6_mul): sums of unreduced 512-bit products ----------------
+// Values are kept mod 2^512 (additions and subtractions wrap); only the FINAL value of each accumulation has to lie
+// in [0, 2^512) = [0, 27.98 p^2), which the caller arranges with one offset k * p * 2^253 (0.661 p^2 per unit).
+SY_DEFINE_TABLE(uint32_t, kWideOff2, 9, 0xc0000000u, 0xb61f3f51u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu)
+SY_DEFINE_TABLE(uint32_t, kWideOff4, 9, 0x80000000u, 0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u)
+SY_DEFINE_TABLE(uint32_t, kWideOff5, 9, 0x60000000u, 0x474e1e4cu, 0x4594578eu, 0xe1471e98u, 0x7eb0e29au, 0x10f0d73au, 0x13322b92u, 0xccbf041au, 0x1e3eb107u)
+SY_DEFINE_TABLE(uint32_t, kWideOff20, 9, 0x80000000u, 0x1d387931u, 0x16515e39u, 0x851c7a61u, 0xfac38a6bu, 0x43c35ce9u, 0x4cc8ae48u, 0x32fc1068u, 0x78fac41fu)
+SY_DEFINE_TABLE(uint32_t, kP2, 8, 0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u)
+SY_DEFINE_TABLE(uint32_t, kP4, 8, 0x61f3f51cu, 0xf082305bu, 0xa1c72a34u, 0x5e05aa45u, 0x06056176u, 0xe14116dau, 0x84c680a6u, 0xc19139cbu)
+
+// a += b, 16 limbs, mod 2^512
+SY_HD void wide_add(uint32_t* a, const uint32_t* b) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %16;\n\t"
+      "addc.cc.u32 %1, %1, %17;\n\t"
+      "addc.cc.u32 %2, %2, %18;\n\t"
+      "addc.cc.u32 %3, %3, %19;\n\t"
+      "addc.cc.u32 %4, %4, %20;\n\t"
+      "addc.cc.u32 %5, %5, %21;\n\t"
+      "addc.cc.u32 %6, %6, %22;\n\t"
+      "addc.cc.u32 %7, %7, %23;\n\t"
+      "addc.cc.u32 %8, %8, %24;\n\t"
+      "addc.cc.u32 %9, %9, %25;\n\t"
+      "addc.cc.u32 %10, %10, %26;\n\t"
+      "addc.cc.u32 %11, %11, %27;\n\t"
+      "addc.cc.u32 %12, %12, %28;\n\t"
+      "addc.cc.u32 %13, %13, %29;\n\t"
+      "addc.cc.u32 %14, %14, %30;\n\t"
+      "addc.u32 %15, %15, %31;"
+      : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+        "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
+        "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 16; i++) {
+    c += (uint64_t)a[i] + b[i];
+    a[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+// a += off * 2^224 for a 9-limb constant (the k * p * 2^253 offsets above), mod 2^512
+SY_HD void wide_add_off(uint32_t* a, const uint32_t* off) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %11;\n\t"
+      "addc.cc.u32 %3, %3, %12;\n\t"
+      "addc.cc.u32 %4, %4, %13;\n\t"
+      "addc.cc.u32 %5, %5, %14;\n\t"
+      "addc.cc.u32 %6, %6, %15;\n\t"
+      "addc.cc.u32 %7, %7, %16;\n\t"
+      "addc.u32 %8, %8, %17;"
+      : "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+      : "r"(off[0]), "r"(off[1]), "r"(off[2]), "r"(off[3]), "r"(off[4]), "r"(off[5]), "r"(off[6]), "r"(off[7]),
+        "r"(off[8]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 9; i++) {
+    c += (uint64_t)a[7 + i] + off[i];
+    a[7 + i] = (uint32_t)c;
+    c >>= 32;
+  }
+#endif
+}
+// a = 9 a mod 2^512
+SY_HD void wide_mul9(uint32_t* a) {
+  uint32_t t[16];
+#pragma unroll
+  for (int i = 15; i > 0; i--) t[i] = (a[i] << 3) | (a[i - 1] >> 29);
+  t[0] = a[0] << 3;
+  wide_add(a, t);
+}
+// a -= k if a >= k (8 limbs)
+SY_HD void fp_cond_sub(uint32_t* a, const uint32_t* k) {
+  uint32_t t[8], borrow;
+#if defined(__CUDA_ARCH__)
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(k[0]), "r"(k[1]),
+        "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]));
+#else
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    int64_t d = (int64_t)a[i] - (int64_t)k[i] + bw;
+    t[i] = (uint32_t)d;
+    bw = d >> 32;
+  }
+  borrow = (uint32_t)bw;
+#endif
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : t[i];
+}
+// T * R^-1 mod p, fully reduced, for a "fat" T: the high half is first brought below p with STEPS conditional
+// subtractions (4p, 2p, p for 3; 2p, p for 2; p for 1), which needs T < 2^STEPS * p * 2^256.
+template <int STEPS>
+SY_HD Fp fp_redc_fat(const uint32_t* T) {
+  uint32_t U[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) U[i] = T[i];
+  if (STEPS >= 3) fp_cond_sub(U + 8, SY_TAB(kP4));
+  if (STEPS >= 2) fp_cond_sub(U + 8, SY_TAB(kP2));
+  if (STEPS >= 1) fp_cond_sub(U + 8, SY_TAB(kP));
+#if defined(SYLOW_HOSTSIM) && !defined(__CUDA_ARCH__)
+  {  // the bound analysis of the caller, checked on every value the host simulation sees: high half < p
+    int64_t bw = 0;
+    for (int i = 0; i < 8; i++) bw = ((int64_t)U[8 + i] - (int64_t)SY_TAB(kP)[i] + bw) >> 32;
+    if (bw == 0) {
+      fprintf(stderr, "fp_redc_fat<%d>: high half >= p\n", STEPS);
+      abort();
+    }
+  }
+#endif
+  return fp_redc_wide(U);
+}
 
 SY_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 

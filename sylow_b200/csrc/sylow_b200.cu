@@ -670,6 +670,7 @@ __global__ void __launch_bounds__(256, 1) k_tower_probe(int iters, const uint32_
     if (OP == 0) a.c0.c0 = fp2_mul(a.c0.c0, b.c0.c0);
     if (OP == 1) a.c0.c0 = fp2_sqr(a.c0.c0);
     if (OP == 2) a.c0 = fp6_mul(a.c0, b.c0);
+    if (OP == 10) a.c0 = fp6_mul_lazy(a.c0, b.c0);
     if (OP == 3) a = fp12_mul(a, b);
     if (OP == 4) a = fp12_sqr(a);
     if (OP == 5) a = fp12_sparse_mul(a, b.c0.c0, b.c0.c1, b.c0.c2);
@@ -2029,6 +2030,7 @@ int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int thre
       case 37: k_tower_probe<7><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 26; break;
       case 38: k_tower_probe<8><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 4; break;
       case 39: k_tower_probe<9><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 2; break;
+      case 44: k_tower_probe<10><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 18; break;
       case 40: k_overlap_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
       case 41: k_overlap_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
       case 42: k_overlap_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;

@@ -144,6 +144,108 @@ SY_HD Fp6 fp6_dbl(const Fp6& a) { return Fp6{fp2_dbl(a.c0), fp2_dbl(a.c1), fp2_d
 SY_HD Fp6 fp6_mul_v(const Fp6& a) { return Fp6{fp2_mul_xi(a.c2), a.c0, a.c1}; }
 SY_HD bool fp6_eq(const Fp6& a, const Fp6& b) { return fp2_eq(a.c0, b.c0) & fp2_eq(a.c1, b.c1) & fp2_eq(a.c2, b.c2); }
 
+// ---- unreduced Fp2 values: (re, im) as 512-bit integers mod 2^512, congruent to the true value mod p ------------
+struct alignas(16) Wide2 {
+  uint32_t c0[16], c1[16];
+};
+// Karatsuba product without any reduction.  Coefficients of a and b may be unreduced sums (< 2p):
+//   c1 = a0 b1 + a1 b0 in [0, 2 p^2) ([0, 8 p^2) for sums);  c0 = a0 b0 - a1 b1 in (-p^2, p^2) ((-4, 4) p^2), WRAPPED mod 2^512
+// (inlined into fp6_mul_lazy: the 512-bit values have to stay in registers - staged through local memory the scheme
+// loses more on L1 traffic than it saves on reductions, profiles/r01_lazy_fp6.md)
+SY_HD void fp2_mul_unr(Wide2& r, const Fp2& a, const Fp2& b) {
+  uint32_t t1[16], sa[8], sb[8];
+  fp_mul_wide(r.c0, a.c0.l, b.c0.l);
+  fp_mul_wide(t1, a.c1.l, b.c1.l);
+  fp_add_nr(sa, a.c0.l, a.c1.l);
+  fp_add_nr(sb, b.c0.l, b.c1.l);
+  fp_mul_wide(r.c1, sa, sb);
+  wide_sub(r.c1, r.c0);
+  wide_sub(r.c1, t1);
+  wide_sub(r.c0, t1);
+}
+SY_HD void wide2_add(Wide2& a, const Wide2& b) {
+  wide_add(a.c0, b.c0);
+  wide_add(a.c1, b.c1);
+}
+SY_HD void wide2_sub(Wide2& a, const Wide2& b) {
+  wide_sub(a.c0, b.c0);
+  wide_sub(a.c1, b.c1);
+}
+// both coefficients through the Montgomery reduction; S0 / S1 = conditional subtractions the high halves need
+template <int S0, int S1>
+SY_HD Fp2 fp2_redc(const Wide2& t) {
+  return Fp2{fp_redc_fat<S0>(t.c0), fp_redc_fat<S1>(t.c1)};
+}
+// coefficient-wise sum without reduction (< 2p for canonical inputs)
+SY_HD Fp2 fp2_add_nr(const Fp2& a, const Fp2& b) {
+  Fp2 r;
+  fp_add_nr(r.c0.l, a.c0.l, b.c0.l);
+  fp_add_nr(r.c1.l, a.c1.l, b.c1.l);
+  return r;
+}
+
+// Measured (profiles/r01_lazy_fp6.md): +6 % on an isolated fp12_sqr, nothing on k_miller, so it is off by default.
+#ifndef SY_LAZY_FP6
+#define SY_LAZY_FP6 0
+#endif
+
+// Karatsuba with lazy reduction above Fp2: the six products stay unreduced and the linear combinations are formed on
+// the 512-bit values, so the product needs 8 Montgomery reductions instead of 12 and no reduced Fp2 additions except
+// the last one.  Bounds in units of p^2 (2^512 = 27.98, p 2^256 = 5.29, one offset unit p 2^253 = 0.661), inputs
+// canonical (the bounds are on the Montgomery representatives, all < p):
+//   V_i = a_i b_i:            re in (-1, 1),  im in [0, 2)
+//   a_i b_j + a_j b_i:        re in (-2, 2),  im in [0, 4)
+//   c2 = a0 b2 + a2 b0 + V1:           re (-3, 3) + 5 units -> (0.3, 6.3);     im [0, 6)        one conditional subtraction
+//   c1 = a0 b1 + a1 b0 + xi V2:        re (-13, 11) + 20 units -> (0.2, 24.3); im (-1, 23) + 2 units -> (0.3, 24.4)   three
+//   c0 = V0 + xi (a1 b2 + a2 b1):      9 * 4 p^2 does not fit, so W = a1 b2 + a2 b1 (re + 4 units < 4.7, im < 4) and V0
+//                                      (re + 2 units < 2.4) are reduced separately and xi is applied to the reduced W.
+// With -DSY_LAZY_FP6=1 fp12_sqr (the Miller loop) uses it.  The final exponentiation keeps the compact fp6_mul below in
+// any case: with this 76 KB body next to the cyclotomic squaring its instruction working set no longer fits (-9 %).
+SY_HD_NOINLINE Fp6 fp6_mul_lazy(const Fp6& a, const Fp6& b) {
+  Wide2 v0, v1, v2, m;
+  Fp6 r;
+  fp2_mul_unr(v0, a.c0, b.c0);
+  fp2_mul_unr(v1, a.c1, b.c1);
+  fp2_mul_unr(v2, a.c2, b.c2);
+  // c0
+  fp2_mul_unr(m, fp2_add_nr(a.c1, a.c2), fp2_add_nr(b.c1, b.c2));
+  wide2_sub(m, v1);
+  wide2_sub(m, v2);
+  wide_add_off(m.c0, SY_TAB(kWideOff4));
+  Fp2 w = fp2_redc<0, 0>(m);
+  m = v0;
+  wide_add_off(m.c0, SY_TAB(kWideOff2));
+  r.c0 = fp2_add(fp2_redc<0, 0>(m), fp2_mul_xi(w));
+  // c1
+  fp2_mul_unr(m, fp2_add_nr(a.c0, a.c1), fp2_add_nr(b.c0, b.c1));
+  wide2_sub(m, v0);
+  wide2_sub(m, v1);
+  wide_sub(m.c0, v2.c1);   // xi V2 = (9 re2 - im2, 9 im2 + re2)
+  wide_add(m.c1, v2.c0);
+  {
+    uint32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = v2.c0[i];
+    wide_mul9(t);
+    wide_add(m.c0, t);
+#pragma unroll
+    for (int i = 0; i < 16; i++) t[i] = v2.c1[i];
+    wide_mul9(t);
+    wide_add(m.c1, t);
+  }
+  wide_add_off(m.c0, SY_TAB(kWideOff20));
+  wide_add_off(m.c1, SY_TAB(kWideOff2));
+  r.c1 = fp2_redc<3, 3>(m);
+  // c2
+  fp2_mul_unr(m, fp2_add_nr(a.c0, a.c2), fp2_add_nr(b.c0, b.c2));
+  wide2_sub(m, v0);
+  wide2_sub(m, v2);
+  wide2_add(m, v1);
+  wide_add_off(m.c0, SY_TAB(kWideOff5));
+  r.c2 = fp2_redc<1, 1>(m);
+  return r;
+}
+
 // Karatsuba, 6 Fp2 products (value-equal to the 36-product schoolbook of fp6.rs:267-368; this is
 // the form the reference quotes in its own comment at fp6.rs:274-283)
 SY_HD_NOINLINE Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
@@ -209,8 +311,13 @@ SY_HD_NOINLINE Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
 SY_HD_NOINLINE Fp12 fp12_sqr(const Fp12& a) {
   Fp6 c0 = fp6_sub(a.c0, a.c1);
   Fp6 c3 = fp6_sub(a.c0, fp6_mul_v(a.c1));
+#if SY_LAZY_FP6
+  Fp6 c2 = fp6_mul_lazy(a.c0, a.c1);
+  c0 = fp6_add(fp6_mul_lazy(c0, c3), c2);
+#else
   Fp6 c2 = fp6_mul(a.c0, a.c1);
   c0 = fp6_add(fp6_mul(c0, c3), c2);
+#endif
   Fp12 r;
   r.c1 = fp6_dbl(c2);
   r.c0 = fp6_add(c0, fp6_mul_v(c2));

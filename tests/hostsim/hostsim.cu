@@ -151,6 +151,14 @@ int hs_svdw_pair(const uint8_t* u0, const uint8_t* u1, uint8_t* out) {
   fp_store(out + 96, y1);
   return ok ? 1 : 0;
 }
+// Fp6 product, classic (lazy = 0) or with lazy reduction above Fp2 (lazy = 1); 192-byte operands
+void hs_fp6_mul(int lazy, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  Fp6 x{fp2_load(a), fp2_load(a + 64), fp2_load(a + 128)}, y{fp2_load(b), fp2_load(b + 64), fp2_load(b + 128)};
+  Fp6 r = lazy ? fp6_mul_lazy(x, y) : fp6_mul(x, y);
+  fp2_store(out, r.c0);
+  fp2_store(out + 64, r.c1);
+  fp2_store(out + 128, r.c2);
+}
 int hs_g1_add(const uint8_t* p, int pinf, const uint8_t* q, int qinf, uint8_t* out) {
   G1Aff a{fp_load(p), fp_load(p + 32), pinf != 0}, b{fp_load(q), fp_load(q + 32), qinf != 0};
   G1Aff r = proj_to_affine(proj_add(affine_to_proj(a), affine_to_proj(b)));

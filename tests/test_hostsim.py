@@ -59,6 +59,31 @@ def _fp12_op(hs, op, a, b=None):
     return w.b_fp12(out.raw)
 
 
+def test_fp12_edge_coefficients(hs):
+    """Extremes of the lazy-reduction bounds (tower.cuh fp6_mul): coefficients from {0, 1, p-1, p-2, ...} in every
+    position; the host build aborts if a high half is not below p before a Montgomery reduction."""
+    rng = random.Random(30)
+    edge = [0, 1, 2, o.P - 1, o.P - 2, (o.P - 1) // 2, (o.P + 1) // 2, (1 << 32) - 1, 1 << 224, (1 << 253) + 1,
+            (1 << 256) % o.P, o.P - ((1 << 256) % o.P)]
+    # the bounds are on the MONTGOMERY representatives: -1/R mod p is stored as p - 1, the largest limb pattern
+    top = o.P - pow(1 << 256, -1, o.P)
+    edge += [top, (o.P - 2) * pow(1 << 256, -1, o.P) % o.P]
+    cases = [([top] * 12, [top] * 12), ([top, 0] * 6, [0, top] * 6), ([0, top] * 6, [0, top] * 6),
+             ([top, 0] * 6, [top, 0] * 6), ([top] * 6 + [0] * 6, [0] * 6 + [top] * 6), ([o.P - 1] * 12, [o.P - 1] * 12)]
+    cases += [([rng.choice(edge) for _ in range(12)], [rng.choice(edge) for _ in range(12)]) for _ in range(60)]
+    cases += [([rng.choice([0, top]) for _ in range(12)], [rng.choice([0, top]) for _ in range(12)]) for _ in range(60)]
+    out = ctypes.create_string_buffer(192)
+    for ca, cb in cases:
+        a, b = o.fp12_from_list(ca), o.fp12_from_list(cb)
+        for lazy in (0, 1):  # fp6_mul and fp6_mul_lazy (8 reductions, bounds asserted in the host build)
+            hs.hs_fp6_mul(lazy, w.fp12_b(a)[:192], w.fp12_b(b)[:192], out)
+            got = w.b_fp12(out.raw + bytes(192))[0]
+            assert got == o.fp6_mul(a[0], b[0]), lazy
+        assert _fp12_op(hs, 0, a, b) == o.fp12_mul(a, b)
+        assert _fp12_op(hs, 1, a) == o.fp12_sqr(a)
+        assert _fp12_op(hs, 7, a, b) == o.fp12_sparse_mul(a, b[0][0], b[0][1], b[0][2])
+
+
 def test_fp12_ops(hs):
     rng = random.Random(2)
     for _ in range(4):
