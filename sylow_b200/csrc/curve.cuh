@@ -114,13 +114,13 @@ SY_HD_NOINLINE Proj<F> proj_add(const Proj<F>& a, const Proj<F>& b) {
 
 template <class F>
 SY_HD Proj<F> affine_to_proj(const Affine<F>& a) {
-  Proj<F> r;
-  r.x = a.x;
-  r.y = a.y;
-  if (a.inf)
-    f_set_zero(r.z);
-  else
+  // a flagged point is (0 : 1 : 0) whatever its coordinate bytes hold (GroupAffine::zero(), group.rs:236-244)
+  Proj<F> r = proj_zero<F>();
+  if (!a.inf) {
+    r.x = a.x;
+    r.y = a.y;
     f_set_one(r.z);
+  }
   return r;
 }
 

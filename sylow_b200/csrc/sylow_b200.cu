@@ -198,15 +198,67 @@ k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
   ok[c] = one ? 1 : 0;
 }
 
+SY_HD void g1_store_proj(uint8_t* p, const G1Proj& q) {
+  fp_store_raw(p, q.x);
+  fp_store_raw(p + 32, q.y);
+  fp_store_raw(p + 64, q.z);
+}
+// Projective (Montgomery form, 96 B) -> affine wire format for a whole batch with Montgomery's trick: thread t owns the
+// SY_AFF_K points t, t + T, t + 2T, ... (coalesced), multiplies their Z together, inverts ONCE and unwinds.  A point at
+// infinity (Z = 0) enters the product as 1 and is written as (0, 1) + flag, like GroupAffine::from (group.rs:475-495).
+#define SY_AFF_K 8
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_g1_batch_affine(const uint8_t* __restrict__ proj, size_t n, int negate, uint8_t* __restrict__ out,
+                  uint8_t* __restrict__ out_inf) {
+  const size_t T = (n + SY_AFF_K - 1) / SY_AFF_K;
+  size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t t = t0 < T ? t0 : T - 1;  // the inversion ladder is block-synchronised: every thread runs it
+  Fp pre[SY_AFF_K];
+  Fp acc = fp_one();
+  for (int j = 0; j < SY_AFF_K; j++) {
+    size_t i = t + (size_t)j * T;
+    Fp z = i < n ? fp_load_raw(proj + i * 96 + 64) : fp_one();
+    z = fp_select(fp_is_zero(z), fp_one(), z);
+    acc = fp_mul(acc, z);
+    pre[j] = acc;
+  }
+  Fp inv = fp_inv(acc);
+  for (int j = SY_AFF_K - 1; j >= 0; j--) {
+    size_t i = t + (size_t)j * T;
+    if (i >= n) continue;  // only the last stride can be short; its z entered the product as 1
+    Fp z = fp_load_raw(proj + i * 96 + 64);
+    bool inf = fp_is_zero(z);
+    z = fp_select(inf, fp_one(), z);
+    Fp zi = j ? fp_mul(inv, pre[j - 1]) : inv;
+    inv = fp_mul(inv, z);
+    if (t0 >= T) continue;
+    Fp x = fp_mul(fp_load_raw(proj + i * 96), zi), y = fp_mul(fp_load_raw(proj + i * 96 + 32), zi);
+    if (inf) {
+      x = fp_zero();
+      y = fp_one();
+    } else if (negate) {
+      y = fp_neg(y);
+    }
+    fp_store(out + i * 64, x);
+    fp_store(out + i * 64 + 32, y);
+    if (out_inf) out_inf[i] = inf;
+  }
+}
+
 __global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
 k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                      const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
-                     uint8_t* __restrict__ out_inf) {
+                     uint8_t* __restrict__ out_inf, uint8_t* __restrict__ proj_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;  // all threads run the (block-synchronised) loops; surplus is discarded
   G1Aff a{fp_load(pts + i * 64), fp_load(pts + i * 64 + 32), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
-  G1Aff r = proj_to_affine(SY_SCALAR_MUL(affine_to_proj(a), k.l));
+  G1Proj q = SY_SCALAR_MUL(affine_to_proj(a), k.l);
+  if (proj_out) {  // large batches: k_g1_batch_affine shares one inversion between eight points
+    if (i0 < n) g1_store_proj(proj_out + i * 96, q);
+    return;
+  }
+  G1Aff r = proj_to_affine(q);
   if (i0 >= n) return;
   fp_store(out + i * 64, r.x);
   fp_store(out + i * 64 + 32, r.y);
@@ -232,12 +284,19 @@ k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
 __global__ void __launch_bounds__(SY_HASH_THREADS, SY_G1_MINB)
 k_hash_to_g1(const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ offsets, size_t n,
              const __grid_constant__ DstPrime dst, int negate, uint8_t* __restrict__ out,
-             uint8_t* __restrict__ out_inf, int* __restrict__ fail_flag) {
+             uint8_t* __restrict__ out_inf, int* __restrict__ fail_flag, uint8_t* __restrict__ proj_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
   uint64_t o0 = offsets[i], o1 = offsets[i + 1];
   G1Proj p;
   bool ok = hash_to_g1(msgs + o0, (size_t)(o1 - o0), dst.b, dst.len, p, dst.hash_id);
+  if (proj_out) {  // large batches: affine conversion (and the negation) in k_g1_batch_affine
+    if (i0 < n) {
+      if (!ok) atomicExch(fail_flag, 1);
+      g1_store_proj(proj_out + i * 96, p);
+    }
+    return;
+  }
   G1Aff r = proj_to_affine(p);
   if (i0 >= n) return;
   if (!ok) atomicExch(fail_flag, 1);
@@ -829,7 +888,7 @@ struct sylow_b200_ctx {
   DevBuf in_a, in_b, in_c, in_d, flag_a, flag_b, out, scratch0, scratch1, scratch2;
   int* d_fail = nullptr;
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
-  DevBuf tables, sum0, sum1;
+  DevBuf tables, sum0, sum1, proj;
   unsigned glued_attr_mask = 0;
 };
 
@@ -909,6 +968,7 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->tables.p) cudaFree(ctx->tables.p);
   if (ctx->sum0.p) cudaFree(ctx->sum0.p);
   if (ctx->sum1.p) cudaFree(ctx->sum1.p);
+  if (ctx->proj.p) cudaFree(ctx->proj.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -1026,13 +1086,29 @@ int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, c
   return 0;
 }
 
+// batches from this size on convert to affine coordinates with one inversion per eight points
+#define SY_AFF_MIN_BATCH 32768
+static int g1_batch_affine(sylow_b200_ctx* ctx, const uint8_t* d_proj, size_t n, int negate, uint8_t* d_out,
+                           uint8_t* d_out_inf, cudaStream_t s) {
+  size_t T = (n + SY_AFF_K - 1) / SY_AFF_K;
+  k_g1_batch_affine<<<nblocks(T, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_proj, n, negate, d_out, d_out_inf);
+  LAUNCHED(ctx);
+  return 0;
+}
+
 int sylow_b200_g1_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf,
                                 const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* out_inf, void* stream) {
   if (!ctx || (n && (!pts || !scalars || !out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
+  uint8_t* proj = nullptr;
+  if (n >= SY_AFF_MIN_BATCH) {
+    CKS(reserve(ctx, ctx->proj, n * 96));
+    proj = ctx->proj.p;
+  }
   k_g1_mul<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, pick(ctx, stream)>>>(pts, pts_inf, scalars, n,
-                                                                                        out, out_inf);
+                                                                                        out, out_inf, proj);
   LAUNCHED(ctx);
+  if (proj) CKS(g1_batch_affine(ctx, proj, n, 0, out, out_inf, pick(ctx, stream)));
   return 0;
 }
 int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf,
@@ -1077,9 +1153,15 @@ static int make_dst_prime(sylow_b200_ctx* ctx, const uint8_t* dst, size_t dst_le
 
 static int hash_launch(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
                        const DstPrime& dp, int negate, uint8_t* d_out, uint8_t* d_out_inf, cudaStream_t s) {
+  uint8_t* proj = nullptr;
+  if (n >= SY_AFF_MIN_BATCH) {
+    CKS(reserve(ctx, ctx->proj, n * 96));
+    proj = ctx->proj.p;
+  }
   k_hash_to_g1<<<nblocks(n, SY_HASH_THREADS), SY_HASH_THREADS, 0, s>>>(d_msgs, d_offsets, n, dp, negate, d_out,
-                                                                     d_out_inf, ctx->d_fail);
+                                                                     d_out_inf, ctx->d_fail, proj);
   LAUNCHED(ctx);
+  if (proj) CKS(g1_batch_affine(ctx, proj, n, negate, d_out, d_out_inf, s));
   return 0;
 }
 

@@ -631,3 +631,39 @@ def test_threshold_signing_flow(eng):
     # t - 1 shares interpolate a different polynomial: the result is not the group signature
     bad, _ = eng.threshold_aggregate_batch(I[:, : t - 1].copy(), S[:, : t - 1].copy())
     assert not any(bytes(b) == bytes(group_sig) for b in bad)
+
+
+def test_batched_affine_conversion(eng):
+    """Batches of 2^15 points and more share one inversion between eight points (k_g1_batch_affine).  The result must be
+    the same bytes as the small-batch path (one inversion per point, checked against the oracle above), including
+    infinite results, infinite inputs, a ragged tail and the negated hashes verify_batch uses."""
+    rs = np.random.RandomState(41)
+    n = 32768 + 5
+    k = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    k[:, 31] &= 0x1F
+    k[[0, 7, 8, 4096, n - 1]] = 0                                  # 0 * P = infinity
+    k[100] = np.frombuffer(o.R_ORDER.to_bytes(32, "little"), dtype=np.uint8)   # r * P = infinity
+    base = arr([w.g1_b(o.G1_GEN)])
+    pts, _ = eng.g1_mul_batch(np.repeat(base, 64, axis=0), rs.randint(1, 255, size=(64, 32), dtype=np.uint8) & 0x1F)
+    P = np.tile(pts, (n // 64 + 1, 1))[:n].copy()
+    pinf = np.zeros(n, np.uint8)
+    pinf[[3, 4097]] = 1
+    out, inf = eng.g1_mul_batch(P, k, pts_inf=pinf)
+    ref, rinf = [], []
+    for s in range(0, n, 8192):
+        a, b = eng.g1_mul_batch(P[s:s + 8192], k[s:s + 8192], pts_inf=pinf[s:s + 8192])
+        ref.append(a)
+        rinf.append(b)
+    assert (out == np.concatenate(ref)).all() and (inf == np.concatenate(rinf)).all()
+    assert inf[[0, 3, 7, 8, 100, 4096, 4097, n - 1]].all() and inf.sum() == 8
+    assert w.b_g1(bytes(out[0]), 1) == (0, 1, True)
+    idx = [1, 2, 9, 4095, n - 2]
+    assert [w.b_g1(bytes(out[i])) for i in idx] == [
+        o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, w.b_g1(bytes(P[i]))),
+                                             int.from_bytes(bytes(k[i]), "little"))) for i in idx]
+    # hash-to-curve through the same conversion, and the signatures built on it
+    msgs = [i.to_bytes(4, "little") * (1 + i % 3) for i in range(n)]
+    h, hinf = eng.hash_to_g1_batch(msgs)
+    hs = np.concatenate([eng.hash_to_g1_batch(msgs[s:s + 8192])[0] for s in range(0, n, 8192)])
+    assert (h == hs).all() and not hinf.any()
+    assert w.b_g1(bytes(h[n - 1])) == o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(msgs[n - 1]))
