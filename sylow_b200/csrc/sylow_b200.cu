@@ -245,6 +245,42 @@ k_g1_batch_affine(const uint8_t* __restrict__ proj, size_t n, int negate, uint8_
   }
 }
 
+// the same for G2 (192-byte projective points, Z in Fp2)
+__global__ void __launch_bounds__(SY_MUL_THREADS, 1)
+k_g2_batch_affine(const uint8_t* __restrict__ proj, size_t n, uint8_t* __restrict__ out, uint8_t* __restrict__ out_inf) {
+  const size_t T = (n + SY_AFF_K - 1) / SY_AFF_K;
+  size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t t = t0 < T ? t0 : T - 1;
+  Fp2 pre[SY_AFF_K];
+  Fp2 acc = fp2_one();
+  for (int j = 0; j < SY_AFF_K; j++) {
+    size_t i = t + (size_t)j * T;
+    Fp2 z = i < n ? fp2_load_raw(proj + i * 192 + 128) : fp2_one();
+    z = fp2_select(fp2_is_zero(z), fp2_one(), z);
+    acc = fp2_mul(acc, z);
+    pre[j] = acc;
+  }
+  Fp2 inv = fp2_inv(acc);
+  for (int j = SY_AFF_K - 1; j >= 0; j--) {
+    size_t i = t + (size_t)j * T;
+    if (i >= n) continue;
+    Fp2 z = fp2_load_raw(proj + i * 192 + 128);
+    bool inf = fp2_is_zero(z);
+    z = fp2_select(inf, fp2_one(), z);
+    Fp2 zi = j ? fp2_mul(inv, pre[j - 1]) : inv;
+    inv = fp2_mul(inv, z);
+    if (t0 >= T) continue;
+    Fp2 x = fp2_mul(fp2_load_raw(proj + i * 192), zi), y = fp2_mul(fp2_load_raw(proj + i * 192 + 64), zi);
+    if (inf) {
+      x = fp2_zero();
+      y = fp2_one();
+    }
+    fp2_store(out + i * 128, x);
+    fp2_store(out + i * 128 + 64, y);
+    if (out_inf) out_inf[i] = inf;
+  }
+}
+
 __global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
 k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                      const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
@@ -268,12 +304,21 @@ k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
 __global__ void __launch_bounds__(SY_MUL_THREADS, 1)
 k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                        const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
-                       uint8_t* __restrict__ out_inf) {
+                       uint8_t* __restrict__ out_inf, uint8_t* __restrict__ proj_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
   G2Aff a{fp2_load(pts + i * 128), fp2_load(pts + i * 128 + 64), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
-  G2Aff r = proj_to_affine(SY_SCALAR_MUL(affine_to_proj(a), k.l));
+  G2Proj q = SY_SCALAR_MUL(affine_to_proj(a), k.l);
+  if (proj_out) {
+    if (i0 < n) {
+      fp2_store_raw(proj_out + i * 192, q.x);
+      fp2_store_raw(proj_out + i * 192 + 64, q.y);
+      fp2_store_raw(proj_out + i * 192 + 128, q.z);
+    }
+    return;
+  }
+  G2Aff r = proj_to_affine(q);
   if (i0 >= n) return;
   fp2_store(out + i * 128, r.x);
   fp2_store(out + i * 128 + 64, r.y);
@@ -1115,9 +1160,19 @@ int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const u
                                 const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* out_inf, void* stream) {
   if (!ctx || (n && (!pts || !scalars || !out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
+  uint8_t* proj = nullptr;
+  if (n >= SY_AFF_MIN_BATCH) {
+    CKS(reserve(ctx, ctx->proj, n * 192));
+    proj = ctx->proj.p;
+  }
   k_g2_mul<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, pick(ctx, stream)>>>(pts, pts_inf, scalars,
-                                                                                          n, out, out_inf);
+                                                                                          n, out, out_inf, proj);
   LAUNCHED(ctx);
+  if (proj) {
+    size_t T = (n + SY_AFF_K - 1) / SY_AFF_K;
+    k_g2_batch_affine<<<nblocks(T, SY_MUL_THREADS), SY_MUL_THREADS, 0, pick(ctx, stream)>>>(proj, n, out, out_inf);
+    LAUNCHED(ctx);
+  }
   return 0;
 }
 

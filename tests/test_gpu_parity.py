@@ -661,6 +661,14 @@ def test_batched_affine_conversion(eng):
     assert [w.b_g1(bytes(out[i])) for i in idx] == [
         o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, w.b_g1(bytes(P[i]))),
                                              int.from_bytes(bytes(k[i]), "little"))) for i in idx]
+    # G2: same check on 2^15 + 3 points
+    m = 32768 + 3
+    q64, _ = eng.g2_mul_batch(np.repeat(arr([w.g2_b(o.G2_GEN)]), 64, axis=0), k[200:264])
+    Q = np.tile(q64, (m // 64 + 1, 1))[:m].copy()
+    out2, inf2 = eng.g2_mul_batch(Q, k[:m])
+    ref2 = [eng.g2_mul_batch(Q[s:s + 8192], k[:m][s:s + 8192]) for s in range(0, m, 8192)]
+    assert (out2 == np.concatenate([a for a, _ in ref2])).all() and (inf2 == np.concatenate([b for _, b in ref2])).all()
+    assert inf2[[0, 7, 8, 100, 4096]].all() and inf2.sum() == 5 and w.b_g2(bytes(out2[0]), 1)[2] is True
     # hash-to-curve through the same conversion, and the signatures built on it
     msgs = [i.to_bytes(4, "little") * (1 + i % 3) for i in range(n)]
     h, hinf = eng.hash_to_g1_batch(msgs)
