@@ -849,6 +849,138 @@ SY_HD Fp fp_redc_fat(const uint32_t* T) {
   return fp_redc_wide(U);
 }
 
+// ---- 9 x + y + t mod p in one pass (the multiplications by xi = 9 + u, tower.cuh) --------------------------------
+// x, y, t < p, so T = 9x + y + t < 11p needs 9 limbs.  The quotient is estimated from the top 32 bits,
+// q = floor(floor(T / 2^226) * 21 / 2^32) in {floor(T/p) - 1, floor(T/p)} (2^34 / 21 is 0.76 % above p / 2^224), and
+// T - q p in [0, 2p) is formed mod 2^256 as T + q (2^256 - p) with one multiplier row, then one conditional subtraction.
+// 8 IMAD.WIDE + about 60 ALU instructions instead of the 120 of three doublings, two additions and their reductions.
+#define SY_NP0 0x278302b9
+#define SY_NP1 0xc3df73e9
+#define SY_NP2 0x978e3572
+#define SY_NP3 0x687e956e
+#define SY_NP4 0x7e7ea7a2
+#define SY_NP5 0x47afba49
+#define SY_NP6 0x1ece5fd6
+#define SY_NP7 0xcf9bb18d
+SY_DEFINE_TABLE(uint32_t, kNegP, 8, SY_NP0, SY_NP1, SY_NP2, SY_NP3, SY_NP4, SY_NP5, SY_NP6, SY_NP7)
+
+// T[0..8] += a[0..7]
+SY_HD void lin9_acc(uint32_t* T, const uint32_t* a) {
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, %10;\n\t"
+      "addc.cc.u32 %2, %2, %11;\n\t"
+      "addc.cc.u32 %3, %3, %12;\n\t"
+      "addc.cc.u32 %4, %4, %13;\n\t"
+      "addc.cc.u32 %5, %5, %14;\n\t"
+      "addc.cc.u32 %6, %6, %15;\n\t"
+      "addc.cc.u32 %7, %7, %16;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)T[i] + a[i];
+    T[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  T[8] += (uint32_t)c;
+#endif
+}
+// T (9 limbs, < 11p) -> canonical residue
+SY_HD Fp lin9_reduce(const uint32_t* T) {
+  uint32_t h = (T[8] << 30) | (T[7] >> 2);
+  Fp r;
+#if defined(__CUDA_ARCH__)
+  uint32_t q = __umulhi(h, 21u);
+  uint32_t e[8], o[8];
+  asm("mad.lo.cc.u32 %0, %8, " SY_STR(SY_NP0) ", %9;\n\t"
+      "madc.hi.cc.u32 %1, %8, " SY_STR(SY_NP0) ", %10;\n\t"
+      "madc.lo.cc.u32 %2, %8, " SY_STR(SY_NP2) ", %11;\n\t"
+      "madc.hi.cc.u32 %3, %8, " SY_STR(SY_NP2) ", %12;\n\t"
+      "madc.lo.cc.u32 %4, %8, " SY_STR(SY_NP4) ", %13;\n\t"
+      "madc.hi.cc.u32 %5, %8, " SY_STR(SY_NP4) ", %14;\n\t"
+      "madc.lo.cc.u32 %6, %8, " SY_STR(SY_NP6) ", %15;\n\t"
+      "madc.hi.u32 %7, %8, " SY_STR(SY_NP6) ", %16;"
+      : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7])
+      : "r"(q), "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]));
+  asm("mul.lo.u32 %0, %7, " SY_STR(SY_NP1) "; mul.hi.u32 %1, %7, " SY_STR(SY_NP1) ";\n\t"
+      "mul.lo.u32 %2, %7, " SY_STR(SY_NP3) "; mul.hi.u32 %3, %7, " SY_STR(SY_NP3) ";\n\t"
+      "mul.lo.u32 %4, %7, " SY_STR(SY_NP5) "; mul.hi.u32 %5, %7, " SY_STR(SY_NP5) ";\n\t"
+      "mul.lo.u32 %6, %7, " SY_STR(SY_NP7) ";"
+      : "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+      : "r"(q));
+  r.l[0] = e[0];
+  asm("add.cc.u32 %0, %7, %14;\n\t"
+      "addc.cc.u32 %1, %8, %15;\n\t"
+      "addc.cc.u32 %2, %9, %16;\n\t"
+      "addc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\t"
+      "addc.cc.u32 %5, %12, %19;\n\t"
+      "addc.u32 %6, %13, %20;"
+      : "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+      : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+        "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+#else
+  uint32_t q = (uint32_t)(((uint64_t)h * 21u) >> 32);
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {  // T + q (2^256 - p) mod 2^256
+    c += (uint64_t)T[i] + (uint64_t)q * SY_TAB(kNegP)[i];
+    r.l[i] = (uint32_t)c;
+    c >>= 32;
+  }
+#if defined(SYLOW_HOSTSIM)
+  {  // the estimate may be one short, never more: T - q p < 2p
+    uint32_t chk[8];
+    for (int i = 0; i < 8; i++) chk[i] = r.l[i];
+    int64_t bw = 0;
+    for (int i = 0; i < 8; i++) bw = ((int64_t)chk[i] - (int64_t)SY_TAB(kP2)[i] + bw) >> 32;
+    if (bw == 0) {
+      fprintf(stderr, "lin9_reduce: remainder >= 2p\n");
+      abort();
+    }
+  }
+#endif
+#endif
+  fp_final_sub(r.l);
+  return r;
+}
+// 9 x + y  and  9 x + y + t   (all operands < p)
+SY_HD void lin9_start(uint32_t* T, const Fp& x) {
+#pragma unroll
+  for (int i = 7; i > 0; i--) T[i] = (x.l[i] << 3) | (x.l[i - 1] >> 29);
+  T[0] = x.l[0] << 3;
+  T[8] = x.l[7] >> 29;
+  lin9_acc(T, x.l);
+}
+SY_HD Fp fp_lin9(const Fp& x, const Fp& y) {
+  uint32_t T[9];
+  lin9_start(T, x);
+  lin9_acc(T, y.l);
+  return lin9_reduce(T);
+}
+SY_HD Fp fp_lin9(const Fp& x, const Fp& y, const Fp& t) {
+  uint32_t T[9];
+  lin9_start(T, x);
+  lin9_acc(T, y.l);
+  lin9_acc(T, t.l);
+  return lin9_reduce(T);
+}
+SY_HD Fp fp_mul9(const Fp& x) {  // 3b = 9 of G1's complete formulas (curve.cuh)
+  uint32_t T[9];
+  lin9_start(T, x);
+  return lin9_reduce(T);
+}
+// p - z without reduction: in (0, p] for z < p (p itself stands for 0 and is a valid fp_lin9 operand)
+SY_HD Fp fp_neg_nr(const Fp& z) {
+  Fp r, pp;
+#pragma unroll
+  for (int i = 0; i < 8; i++) pp.l[i] = SY_TAB(kP)[i];
+  fp_sub_nr(r.l, pp.l, z.l);
+  return r;
+}
+
 SY_HD Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }
 
 SY_HD Fp fp_to_mont(const Fp& a) { return fp_mul(fp_R2(), a); }  // any a < 2^256 (reduces mod p)
@@ -860,10 +992,6 @@ SY_HD Fp fp_from_mont(const Fp& a) {
 
 // small-constant helpers (additions only)
 SY_HD Fp fp_mul3(const Fp& a) { return fp_add(fp_dbl(a), a); }
-SY_HD Fp fp_mul9(const Fp& a) {
-  Fp t = fp_dbl(fp_dbl(fp_dbl(a)));
-  return fp_add(t, a);
-}
 
 // a^e for a fixed 256-bit exponent given as 8 LE words (uniform across the warp); top_bit = index of its
 // highest set bit.  Fixed 4-bit windows: 14 multiplications for the table, then 4 squarings and at most one

@@ -194,7 +194,7 @@ SY_HD_NOINLINE Fp12 fp12_frobenius(const Fp12& a, int e) {
 SY_HD void fp4_square(const Fp2& a, const Fp2& b, Fp2& c0, Fp2& c1) {
   Fp2 t0 = fp2_sqr(a);
   Fp2 t1 = fp2_sqr(b);
-  c0 = fp2_add(fp2_mul_xi(t1), t0);
+  c0 = fp2_mul_xi_add(t1, t0);
   c1 = fp2_sub(fp2_sub(fp2_sqr(fp2_add(a, b)), t0), t1);
 }
 

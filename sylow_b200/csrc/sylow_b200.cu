@@ -664,6 +664,10 @@ __global__ void __launch_bounds__(128) k_g1_segment_sum(const uint8_t* __restric
   }
 }
 
+SY_HD Fp fp_final_sub_copy(Fp a) {  // p -> 0, anything below p unchanged
+  fp_final_sub(a.l);
+  return a;
+}
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
@@ -674,6 +678,13 @@ __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, ui
     case 2: r = fp_sub(x, y); break;
     case 3: r = fp_inv(x); break;
     case 4: r = fp_halve(x); break;
+    case 8:  // raw limbs in and out: 9 a + b and 9 a + b + b mod p for operands <= p (fp_lin9)
+    case 9: {
+      Fp xr = fp_load_raw(a + i * 32), yr = fp_load_raw(b + i * 32);
+      r = op == 8 ? fp_lin9(xr, yr) : fp_lin9(xr, yr, fp_final_sub_copy(yr));
+      if (i0 < n) fp_store_raw(out + i * 32, r);
+      return;
+    }
     default: r = fp_neg(x);
   }
   if (i0 >= n) return;

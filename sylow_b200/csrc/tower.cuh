@@ -61,9 +61,33 @@ SY_HD Fp2 fp2_select(bool c, const Fp2& a, const Fp2& b) {
 SY_HD_ADD Fp2 fp2_halve(const Fp2& a) { return Fp2{fp_halve(a.c0), fp_halve(a.c1)}; }
 
 // (a0 + a1 u)(9 + u) = (9 a0 - a1) + (a0 + 9 a1) u    (fp2.rs:99-107)
+#ifndef SY_XI_LIN9
+#define SY_XI_LIN9 1
+#endif
 SY_HD_ADD Fp2 fp2_mul_xi(const Fp2& a) {
+#if SY_XI_LIN9
+  return Fp2{fp_lin9(a.c0, fp_neg_nr(a.c1)), fp_lin9(a.c1, a.c0)};
+#else
   Fp t0 = fp_mul9(a.c0), t1 = fp_mul9(a.c1);
   return Fp2{fp_sub(t0, a.c1), fp_add(t1, a.c0)};
+#endif
+}
+// t + xi a and t - xi a: the addition rides in the same reduction
+SY_HD_ADD Fp2 fp2_mul_xi_add(const Fp2& a, const Fp2& t) {
+#if SY_XI_LIN9
+  return Fp2{fp_lin9(a.c0, fp_neg_nr(a.c1), t.c0), fp_lin9(a.c1, a.c0, t.c1)};
+#else
+  return fp2_add(fp2_mul_xi(a), t);
+#endif
+}
+SY_HD_ADD Fp2 fp2_sub_mul_xi(const Fp2& t, const Fp2& a) {
+#if SY_XI_LIN9
+  // (t0 - 9 a0 + a1, t1 - 9 a1 - a0) = (9 (p - a0) + a1 + t0, 9 (p - a1) + (p - a0) + t1)
+  Fp n0 = fp_neg_nr(a.c0), n1 = fp_neg_nr(a.c1);
+  return Fp2{fp_lin9(n0, a.c1, t.c0), fp_lin9(n1, n0, t.c1)};
+#else
+  return fp2_sub(t, fp2_mul_xi(a));
+#endif
 }
 
 // Karatsuba with lazy reduction: 3 full 512-bit products, the linear combinations on the unreduced
@@ -215,7 +239,7 @@ SY_HD_NOINLINE Fp6 fp6_mul_lazy(const Fp6& a, const Fp6& b) {
   Fp2 w = fp2_redc<0, 0>(m);
   m = v0;
   wide_add_off(m.c0, SY_TAB(kWideOff2));
-  r.c0 = fp2_add(fp2_redc<0, 0>(m), fp2_mul_xi(w));
+  r.c0 = fp2_mul_xi_add(w, fp2_redc<0, 0>(m));
   // c1
   fp2_mul_unr(m, fp2_add_nr(a.c0, a.c1), fp2_add_nr(b.c0, b.c1));
   wide2_sub(m, v0);
@@ -253,9 +277,9 @@ SY_HD_NOINLINE Fp6 fp6_mul(const Fp6& a, const Fp6& b) {
   Fp2 t1 = fp2_mul(a.c1, b.c1);
   Fp2 t2 = fp2_mul(a.c2, b.c2);
   Fp2 r0 = fp2_mul(fp2_add(a.c1, a.c2), fp2_add(b.c1, b.c2));
-  r0 = fp2_add(fp2_mul_xi(fp2_sub(fp2_sub(r0, t1), t2)), t0);
+  r0 = fp2_mul_xi_add(fp2_sub(fp2_sub(r0, t1), t2), t0);
   Fp2 r1 = fp2_mul(fp2_add(a.c0, a.c1), fp2_add(b.c0, b.c1));
-  r1 = fp2_add(fp2_sub(fp2_sub(r1, t0), t1), fp2_mul_xi(t2));
+  r1 = fp2_mul_xi_add(t2, fp2_sub(fp2_sub(r1, t0), t1));
   Fp2 r2 = fp2_mul(fp2_add(a.c0, a.c2), fp2_add(b.c0, b.c2));
   r2 = fp2_sub(fp2_add(fp2_sub(r2, t0), t1), t2);
   return Fp6{r0, r1, r2};
@@ -269,8 +293,8 @@ SY_HD_NOINLINE Fp6 fp6_sqr(const Fp6& a) {
   Fp2 s3 = fp2_dbl(fp2_mul(a.c1, a.c2));
   Fp2 s4 = fp2_sqr(a.c2);
   Fp6 r;
-  r.c0 = fp2_add(t0, fp2_mul_xi(s3));
-  r.c1 = fp2_add(t1, fp2_mul_xi(s4));
+  r.c0 = fp2_mul_xi_add(s3, t0);
+  r.c1 = fp2_mul_xi_add(s4, t1);
   r.c2 = fp2_sub(fp2_sub(fp2_add(fp2_add(t1, t2), s3), t0), s4);
   return r;
 }
@@ -302,7 +326,7 @@ SY_HD_NOINLINE Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
   Fp6 t1 = fp6_mul(a.c1, b.c1);
   Fp6 s = fp6_mul(fp6_add(a.c0, a.c1), fp6_add(b.c0, b.c1));
   Fp12 r;
-  r.c0 = fp6_add(fp6_mul_v(t1), t0);
+  r.c0 = Fp6{fp2_mul_xi_add(t1.c2, t0.c0), fp2_add(t1.c0, t0.c1), fp2_add(t1.c1, t0.c2)};  // v t1 + t0
   r.c1 = fp6_sub(fp6_sub(s, t0), t1);
   return r;
 }
@@ -310,7 +334,7 @@ SY_HD_NOINLINE Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
 // complex squaring (fp12.rs:536-550)
 SY_HD_NOINLINE Fp12 fp12_sqr(const Fp12& a) {
   Fp6 c0 = fp6_sub(a.c0, a.c1);
-  Fp6 c3 = fp6_sub(a.c0, fp6_mul_v(a.c1));
+  Fp6 c3{fp2_sub_mul_xi(a.c0.c0, a.c1.c2), fp2_sub(a.c0.c1, a.c1.c0), fp2_sub(a.c0.c2, a.c1.c1)};  // a0 - v a1
 #if SY_LAZY_FP6
   Fp6 c2 = fp6_mul_lazy(a.c0, a.c1);
   c0 = fp6_add(fp6_mul_lazy(c0, c3), c2);
@@ -320,7 +344,7 @@ SY_HD_NOINLINE Fp12 fp12_sqr(const Fp12& a) {
 #endif
   Fp12 r;
   r.c1 = fp6_dbl(c2);
-  r.c0 = fp6_add(c0, fp6_mul_v(c2));
+  r.c0 = Fp6{fp2_mul_xi_add(c2.c2, c0.c0), fp2_add(c2.c0, c0.c1), fp2_add(c2.c1, c0.c2)};  // c0 + v c2
   return r;
 }
 
@@ -339,27 +363,27 @@ SY_HD_NOINLINE Fp12 fp12_sparse_mul(const Fp12& f, const Fp2& x0, const Fp2& x4 
   Fp2 d2 = fp2_mul(z2, x2);
   Fp2 d4 = fp2_mul(z4, x4);
   Fp2 s1 = fp2_mul(z1, x2);
-  r.c0.c0 = fp2_add(fp2_mul_xi(fp2_add(s1, d4)), d0);
+  r.c0.c0 = fp2_mul_xi_add(fp2_add(s1, d4), d0);
   Fp2 t3 = fp2_mul(z5, x4);
   s1 = fp2_add(s1, t3);
-  Fp2 t4 = fp2_mul_xi(fp2_add(t3, d2));
+  Fp2 t4 = fp2_add(t3, d2);
   t3 = fp2_mul(z1, x0);
   s1 = fp2_add(s1, t3);
-  r.c0.c1 = fp2_add(t4, t3);
+  r.c0.c1 = fp2_mul_xi_add(t4, t3);
   t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z2), fp2_add(x0, x2)), d0), d2);
   t4 = fp2_mul(z3, x4);
   s1 = fp2_add(s1, t4);
   r.c0.c2 = fp2_add(t3, t4);
   t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z2, z4), fp2_add(x2, x4)), d2), d4);
-  t4 = fp2_mul_xi(t3);
+  t4 = t3;
   t3 = fp2_mul(z3, x0);
   s1 = fp2_add(s1, t3);
-  r.c1.c0 = fp2_add(t4, t3);
+  r.c1.c0 = fp2_mul_xi_add(t4, t3);
   t3 = fp2_mul(z5, x2);
   s1 = fp2_add(s1, t3);
-  t4 = fp2_mul_xi(t3);
+  t4 = t3;
   t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z4), fp2_add(x0, x4)), d0), d4);
-  r.c1.c1 = fp2_add(t4, t3);
+  r.c1.c1 = fp2_mul_xi_add(t4, t3);
   Fp2 s0 = fp2_add(fp2_add(z1, z3), z5);
   Fp2 t0 = fp2_add(fp2_add(x0, x2), x4);
   r.c1.c2 = fp2_sub(fp2_mul(s0, t0), s1);

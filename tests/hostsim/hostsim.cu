@@ -159,6 +159,11 @@ void hs_fp6_mul(int lazy, const uint8_t* a, const uint8_t* b, uint8_t* out) {
   fp2_store(out + 64, r.c1);
   fp2_store(out + 128, r.c2);
 }
+// fp_lin9 on RAW limb values (no Montgomery conversion): out = 9 x + y (+ t) mod p, operands <= p
+void hs_lin9(const uint8_t* x, const uint8_t* y, const uint8_t* t, int with_t, uint8_t* out) {
+  Fp r = with_t ? fp_lin9(fp_load_raw(x), fp_load_raw(y), fp_load_raw(t)) : fp_lin9(fp_load_raw(x), fp_load_raw(y));
+  fp_store_raw(out, r);
+}
 int hs_g1_add(const uint8_t* p, int pinf, const uint8_t* q, int qinf, uint8_t* out) {
   G1Aff a{fp_load(p), fp_load(p + 32), pinf != 0}, b{fp_load(q), fp_load(q + 32), qinf != 0};
   G1Aff r = proj_to_affine(proj_add(affine_to_proj(a), affine_to_proj(b)));

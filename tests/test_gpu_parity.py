@@ -53,6 +53,33 @@ def test_fp_mul_reference_vectors(eng, kats):
     assert ints(got) == [c[2] for c in cs]
 
 
+def test_lin9(eng):
+    """fp_lin9 (9x + y + t mod p with an estimated quotient, the xi multiplications) on raw limbs: every residue
+    boundary k p - 1, k p, k p + 1 and extreme operands through the PTX path."""
+    rng = random.Random(82)
+    P = o.P
+    xs, ys = [0, P - 1, P - 1, P, 1], [0, P, P - 1, P, P]
+    for k in range(1, 11):
+        for d in (-1, 0, 1):
+            T = k * P + d
+            x = min(P - 1, T // 9)
+            if 0 <= T - 9 * x <= P:
+                xs.append(x)
+                ys.append(T - 9 * x)
+            # three-operand form 9x + y + (y mod p)
+            x = min(P - 1, max(0, (T - 2 * (P - 1)) // 9 + 1))
+            rest = T - 9 * x
+            if rest >= 0 and rest % 2 == 0 and rest // 2 < P:
+                xs.append(x)
+                ys.append(rest // 2)
+    for _ in range(4000):
+        xs.append(rng.randrange(P))
+        ys.append(rng.randrange(P + 1))
+    A, B = arr([w.fp_b(x) for x in xs]), arr([w.fp_b(y) for y in ys])
+    assert ints(eng.fp_op_batch(8, A, B)) == [(9 * x + y) % P for x, y in zip(xs, ys)]
+    assert ints(eng.fp_op_batch(9, A, B)) == [(9 * x + y + y % P) % P for x, y in zip(xs, ys)]
+
+
 def test_fp12_ops(eng):
     rng = random.Random(12)
     n = 6

@@ -59,6 +59,31 @@ def _fp12_op(hs, op, a, b=None):
     return w.b_fp12(out.raw)
 
 
+def test_lin9(hs):
+    """9 x + y + t mod p with the quotient estimated from the top bits (the xi multiplications): every residue
+    boundary k p - 1, k p, k p + 1 and the extreme operands, on raw limb values."""
+    rng = random.Random(81)
+    out = ctypes.create_string_buffer(32)
+    b = lambda v: v.to_bytes(32, "little")
+    P = o.P
+    cases = [(0, 0, 0), (P - 1, P, P - 1), (P - 1, P - 1, P - 1), (P, P, 0), (1, P, 0), (0, P, P - 1)]
+    for k in range(1, 11):  # land T = 9x + y + t on k p - 1, k p, k p + 1
+        for d in (-1, 0, 1):
+            T = k * P + d
+            x = min(P - 1, T // 9)
+            rest = T - 9 * x
+            y = min(P, rest)
+            t = rest - y
+            if 0 <= t < P:
+                cases.append((x, y, t))
+    cases += [(rng.randrange(P), rng.randrange(P + 1), rng.randrange(P)) for _ in range(3000)]
+    for x, y, t in cases:
+        hs.hs_lin9(b(x), b(y), b(t), 1, out)
+        assert int.from_bytes(out.raw, "little") == (9 * x + y + t) % P, (hex(x), hex(y), hex(t))
+        hs.hs_lin9(b(x), b(y), b(0), 0, out)
+        assert int.from_bytes(out.raw, "little") == (9 * x + y) % P
+
+
 def test_fp12_edge_coefficients(hs):
     """Extremes of the lazy-reduction bounds (tower.cuh fp6_mul): coefficients from {0, 1, p-1, p-2, ...} in every
     position; the host build aborts if a high half is not below p before a Montgomery reduction."""
