@@ -29,7 +29,7 @@ FP_MUL_FINAL_EXP = 8822 + 380         # final exponentiation + one Fermat invers
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_miller launch at 2^20 pairs, from the committed
 # `ncu --set full` capture profiles/r01h_k_miller_2pow20.json (local-memory frame spill traffic; the
 # algorithmic bytes are 576 B per pairing: this kernel is bound by the integer-multiply pipe, not by HBM - the
-# 97.5 GB are evictions of the 2.8 KB/thread frame from L2, 474 GB/s or 7 % of the measured HBM bandwidth).
+# 99.1 GB are write-backs of the 2.8 KB/thread frame from L2, 507 GB/s or 8 % of the measured HBM bandwidth).
 NCU_DRAM_BYTES_K_MILLER_2POW20 = 99.10e9
 
 
