@@ -255,6 +255,94 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul_glv(const Proj<F>& p, const uint32_t* k) 
   return acc;
 }
 
+// psi on a projective point (also used by the subgroup check below)
+SY_HD G2Proj g2_psi_1(const G2Proj& q) {
+  return G2Proj{fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q.x)), fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q.y)), fp2_conj(q.z)};
+}
+// ---- 4-dimensional GLS scalar multiplication on G2 ----------------------------------------------------
+// psi (g2.rs:140-152) acts on the r-torsion of the twist as multiplication by mu = p mod r = 6 x^2, so
+// k = k0 + k1 mu + k2 mu^2 + k3 mu^3 with |k_j| < 2^67 (Galbraith-Scott basis, Babai rounding with precomputed
+// 320-bit-scaled cofactors; constants.cuh) needs 64 doublings instead of GLV's 128.
+SY_HD void mp_add256(uint32_t* r, const uint32_t* a, int n) {
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)r[i] + (i < n ? a[i] : 0u);
+    r[i] = (uint32_t)c;
+    c >>= 32;
+  }
+}
+// two's complement 256-bit value -> magnitude (3 limbs: < 2^67 here) and sign
+SY_HD bool mp_abs96(uint32_t* mag, const uint32_t* v) {
+  bool neg = (v[7] >> 31) != 0;
+  uint32_t carry = neg ? 1u : 0u, m = neg ? 0xFFFFFFFFu : 0u;
+  for (int i = 0; i < 3; i++) {
+    uint64_t s = (uint64_t)(v[i] ^ m) + carry;
+    mag[i] = (uint32_t)s;
+    carry = (uint32_t)(s >> 32);
+  }
+  return neg;
+}
+template <int NC>
+SY_HD void gls_apply_row(uint32_t acc[4][8], const uint32_t* c, int i) {
+  for (int j = 0; j < 4; j++) {
+    uint32_t t[NC + 3];
+    mp_mul<NC, 3>(t, c, SY_TAB(kGlsB) + 3 * (4 * i + j));
+    if ((SY_GLS_SUBMASK >> (4 * i + j)) & 1u)
+      mp_sub256(acc[j], t, NC + 3);
+    else
+      mp_add256(acc[j], t, NC + 3);
+  }
+}
+SY_HD void gls_decompose(const uint32_t* k, uint32_t mag[4][3], bool neg[4]) {
+  uint32_t acc[4][8], t[17];
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 8; i++) acc[j][i] = j == 0 ? k[i] : 0u;
+  mp_mul<8, 6>(t, k, SY_TAB(kGlsG0));
+  gls_apply_row<4>(acc, t + 10, 0);
+  mp_mul<8, 9>(t, k, SY_TAB(kGlsG1));
+  gls_apply_row<7>(acc, t + 10, 1);
+  mp_mul<8, 8>(t, k, SY_TAB(kGlsG2));
+  gls_apply_row<6>(acc, t + 10, 2);
+  mp_mul<8, 6>(t, k, SY_TAB(kGlsG3));
+  gls_apply_row<4>(acc, t + 10, 3);
+  for (int j = 0; j < 4; j++) neg[j] = mp_abs96(mag[j], acc[j]);
+}
+// psi^e of a projective point, e = 0..3 (conjugation is the p-power Frobenius of Fp2; the constants are
+// xi^((p-1)/3), xi^((p-1)/2) and their products with their own norms)
+SY_HD G2Proj g2_psi_pow(const G2Proj& q, int e) {
+  switch (e) {
+    case 1: return g2_psi_1(q);
+    case 2: return G2Proj{fp2_mul_fp(q.x, SY_TAB(kPsi2X)[0]), fp2_mul_fp(q.y, SY_TAB(kPsi2Y)[0]), q.z};
+    case 3: return G2Proj{fp2_mul(SY_TAB(kPsi3X)[0], fp2_conj(q.x)), fp2_mul(SY_TAB(kPsi3Y)[0], fp2_conj(q.y)), fp2_conj(q.z)};
+    default: return q;
+  }
+}
+SY_HD_NOINLINE G2Proj g2_scalar_mul_gls(const G2Proj& p, const uint32_t* k) {
+  uint32_t mag[4][3];
+  bool neg[4];
+  gls_decompose(k, mag, neg);
+  G2Proj tab[16];
+  tab[0] = proj_zero<Fp2>();
+  tab[1] = p;
+  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
+  G2Proj acc = proj_zero<Fp2>();
+  for (int w = 16; w >= 0; w--) {
+    SY_LOOP_SYNC();
+    if (w != 16) {
+      acc = proj_double(acc);
+      acc = proj_double(acc);
+      acc = proj_double(acc);
+      acc = proj_double(acc);
+    }
+    for (int e = 0; e < 4; e++) {
+      G2Proj t = g2_psi_pow(tab[(mag[e][w >> 3] >> ((w & 7) * 4)) & 15u], e);
+      if (neg[e]) t.y = fp2_neg(t.y);
+      acc = proj_add(acc, t);
+    }
+  }
+  return acc;
+}
+
 // y^2 == x^3 + b
 SY_HD bool g1_on_curve(const Fp& x, const Fp& y) {
   Fp rhs = fp_add(fp_mul(fp_sqr(x), x), SY_TAB(kFpThree)[0]);
@@ -269,9 +357,7 @@ SY_HD bool g2_on_curve(const Fp2& x, const Fp2& y) {
 // ---- input validation ------------------------------------------------------------
 // psi on a projective point: (eps0 * conj(x), eps1 * conj(y), conj(z)) - the same point the reference
 // reaches through affine coordinates (g2.rs:140-152, :207-210).
-SY_HD G2Proj g2_psi(const G2Proj& q) {
-  return G2Proj{fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q.x)), fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q.y)), fp2_conj(q.z)};
-}
+SY_HD G2Proj g2_psi(const G2Proj& q) { return g2_psi_1(q); }
 // cross-multiplied projective equality (group.rs:426-447)
 SY_HD bool g2_proj_eq(const G2Proj& a, const G2Proj& b) {
   bool az = fp2_is_zero(a.z), bz = fp2_is_zero(b.z);

@@ -22,6 +22,10 @@ using namespace sylow;
 #ifndef SY_GLV
 #define SY_GLV 1
 #endif
+// G2 additionally has the 4-dimensional GLS split (psi); -DSY_GLS=0 falls back to SY_SCALAR_MUL
+#ifndef SY_GLS
+#define SY_GLS 1
+#endif
 #if SY_GLV
 #define SY_SCALAR_MUL proj_scalar_mul_glv
 #else
@@ -309,7 +313,11 @@ k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
   size_t i = i0 < n ? i0 : n - 1;
   G2Aff a{fp2_load(pts + i * 128), fp2_load(pts + i * 128 + 64), pts_inf && pts_inf[i]};
   Fp k = fp_load_raw(scalars + i * 32);
+#if SY_GLS
+  G2Proj q = g2_scalar_mul_gls(affine_to_proj(a), k.l);
+#else
   G2Proj q = SY_SCALAR_MUL(affine_to_proj(a), k.l);
+#endif
   if (proj_out) {
     if (i0 < n) {
       fp2_store_raw(proj_out + i * 192, q.x);

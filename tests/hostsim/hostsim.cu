@@ -111,6 +111,23 @@ int hs_g2_mul_glv(const uint8_t* pt, int inf, const uint8_t* k, uint8_t* out) {
   fp2_store(out + 64, r.y);
   return r.inf;
 }
+int hs_g2_mul_gls(const uint8_t* pt, int inf, const uint8_t* k, uint8_t* out) {
+  G2Aff a{fp2_load(pt), fp2_load(pt + 64), inf != 0};
+  Fp kk = fp_load_raw(k);
+  G2Aff r = proj_to_affine(g2_scalar_mul_gls(affine_to_proj(a), kk.l));
+  fp2_store(out, r.x);
+  fp2_store(out + 64, r.y);
+  return r.inf;
+}
+// out: four magnitudes of 12 bytes LE; return bit j = k_j negative
+int hs_gls_decompose(const uint8_t* k, uint8_t* out) {
+  Fp kk = fp_load_raw(k);
+  uint32_t mag[4][3];
+  bool neg[4];
+  gls_decompose(kk.l, mag, neg);
+  memcpy(out, mag, 48);
+  return (neg[0] ? 1 : 0) | (neg[1] ? 2 : 0) | (neg[2] ? 4 : 0) | (neg[3] ? 8 : 0);
+}
 // out: |k1| (16 bytes LE), |k2| (16 bytes LE); return bit0 = k1 negative, bit1 = k2 negative
 int hs_glv_decompose(const uint8_t* k, uint8_t* out) {
   Fp kk = fp_load_raw(k);

@@ -261,7 +261,10 @@ def test_scalar_mul(eng, kats):
     assert [w.b_g1(bytes(r), i) for r, i in zip(out, inf)] == ref
     n = 24
     qs = [w.rand_g2(rng) for _ in range(n)]
-    ks = [0, 1, o.R_ORDER - 1, o.P - 1, lam, o.R_ORDER, (1 << 256) - 1] + [rng.randrange(1 << 256) for _ in range(n - 7)]
+    mu = o.P % o.R_ORDER  # eigenvalue of psi, the base of the 4-dimensional GLS split (curve.cuh)
+    ks = [0, 1, o.R_ORDER - 1, o.P - 1, lam, o.R_ORDER, (1 << 256) - 1, mu, mu + 1, mu * mu % o.R_ORDER, pow(mu, 3, o.R_ORDER),
+          1 << 64, (1 << 128) - 1]
+    ks += [rng.randrange(1 << 256) for _ in range(n - len(ks))]
     out, inf = eng.g2_mul_batch(arr([w.g2_b(q) for q in qs]), arr([w.fp_b(k) for k in ks]))
     ref = [o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), red(k))) for q, k in zip(qs, ks)]
     assert [w.b_g2(bytes(r), i) for r, i in zip(out, inf)] == ref

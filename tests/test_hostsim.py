@@ -181,6 +181,29 @@ def test_glv_decompose(hs):
         assert abs(k1) < 2**127 and abs(k2) < 2**127, hex(k)
 
 
+def test_gls_decompose_and_mul(hs):
+    """4-dimensional GLS on G2: k = sum k_j mu^j (mod r), mu = 6 x^2 = p mod r, |k_j| < 2^67, and the ladder
+    equals the oracle's k * Q."""
+    rng = random.Random(83)
+    mu = 6 * 4965661367192848881 ** 2
+    assert mu == o.P % o.R_ORDER
+    out = ctypes.create_string_buffer(48)
+    edge = [0, 1, 2, mu, mu + 1, mu * mu % o.R_ORDER, o.R_ORDER - 1, o.R_ORDER, o.R_ORDER + 1, o.P - 1, 2**256 - 1, 2**255,
+            2**64, 2**128 - 1]
+    for k in edge + [rng.randrange(2**256) for _ in range(3000)] + [rng.randrange(o.R_ORDER) for _ in range(1000)]:
+        s = hs.hs_gls_decompose(k.to_bytes(32, "little"), out)
+        ks = [int.from_bytes(out.raw[12 * j: 12 * j + 12], "little") * (-1 if (s >> j) & 1 else 1) for j in range(4)]
+        assert (sum(kj * pow(mu, j, o.R_ORDER) for j, kj in enumerate(ks)) - k) % o.R_ORDER == 0, hex(k)
+        assert all(abs(kj) < 2**67 for kj in ks), hex(k)
+    q = w.rand_g2(rng)
+    out = ctypes.create_string_buffer(128)
+    for k in edge[:11] + [rng.randrange(2**256) for _ in range(4)]:
+        inf = hs.hs_g2_mul_gls(w.g2_b(q), 0, k.to_bytes(32, "little"), out)
+        ref = o.proj_to_affine(o.Fp2Ops, o.proj_mul(o.Fp2Ops, o.affine_to_proj(o.Fp2Ops, q), k % o.R_ORDER))
+        assert w.b_g2(out.raw, inf) == ref, hex(k)
+    assert hs.hs_g2_mul_gls(w.g2_b(((0, 0), (1, 0))), 1, (5).to_bytes(32, "little"), out) == 1
+
+
 def test_scalar_mul_glv(hs):
     """GLV ladder == the oracle's k * P on both groups (affine result)."""
     rng = random.Random(78)
