@@ -278,11 +278,38 @@ SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
 // exponentiation output).  The reference runs a 256-digit NAF ladder with Fp12 squarings; the value g^k does
 // not depend on the chain, so this uses fixed 4-bit windows with cyclotomic squarings and no data-dependent
 // control flow.
+#ifndef SY_GT_GLS
+#define SY_GT_GLS 1
+#endif
 SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
   Fp12 tab[16];
   tab[0] = fp12_one();
   tab[1] = g;
   for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? fp12_mul(tab[i - 1], g) : cyclotomic_squared(tab[i >> 1]);
+#if SY_GT_GLS
+  // g^p is the Frobenius map and p = mu (mod r), the order of Gt: the G2 decomposition k = sum k_j mu^j (curve.cuh)
+  // turns the exponentiation into 17 windows of 4 cyclotomic squarings and 4 multiplications by frobenius^j(tab[d_j]);
+  // a negative k_j multiplies by the conjugate (the inverse on the cyclotomic subgroup).
+  uint32_t mag[4][3];
+  bool neg[4];
+  gls_decompose(k, mag, neg);
+  Fp12 acc = fp12_one();
+  for (int w = 16; w >= 0; w--) {
+    SY_LOOP_SYNC();
+    if (w != 16) {
+      acc = cyclotomic_squared(acc);
+      acc = cyclotomic_squared(acc);
+      acc = cyclotomic_squared(acc);
+      acc = cyclotomic_squared(acc);
+    }
+    for (int e = 0; e < 4; e++) {
+      Fp12 t = tab[(mag[e][w >> 3] >> ((w & 7) * 4)) & 15u];
+      if (e) t = fp12_frobenius(t, e);
+      acc = fp12_mul(acc, neg[e] ? fp12_conj(t) : t);
+    }
+  }
+  return acc;
+#else
   Fp12 acc = tab[k[7] >> 28];
   for (int w = 62; w >= 0; w--) {
     SY_LOOP_SYNC();
@@ -294,6 +321,7 @@ SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
     acc = fp12_mul(acc, tab[d]);
   }
   return acc;
+#endif
 }
 
 }  // namespace sylow

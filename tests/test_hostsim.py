@@ -351,7 +351,8 @@ def test_gt_pow(hs):
     rng = random.Random(8)
     g = o.pairing_affine(o.G1_GEN, o.G2_GEN)
     out = ctypes.create_string_buffer(384)
-    for k in (0, 1, 2, o.R_ORDER - 1, rng.randrange(o.R_ORDER)):
+    mu = o.P % o.R_ORDER  # the exponent is split over the Frobenius eigenvalue (4-dimensional GLS, pairing.cuh)
+    for k in (0, 1, 2, o.R_ORDER - 1, mu, mu * mu % o.R_ORDER, mu - 1, rng.randrange(o.R_ORDER), rng.randrange(o.R_ORDER)):
         hs.hs_gt_pow(w.fp12_b(g), w.fp_b(k), out)
         assert w.b_fp12(out.raw) == o.gt_mul(g, k)
 
