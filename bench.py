@@ -377,6 +377,31 @@ def main():
         eng.threshold_aggregate_batch(ids, h_sig)
         extras["threshold_aggregations_per_s"] = world * ns / max_over_ranks(time.perf_counter() - t0)
         extras["threshold_shares_per_set"] = tt
+        # SURVEY 8(f) ranks 1-3 through the host-pointer calls (wall clock, copies included; 2^17 items, 2^15 for Gt)
+        def wall(fn):
+            fn()
+            t0 = time.perf_counter()
+            fn()
+            return max_over_ranks(time.perf_counter() - t0)
+
+        nx = min(1 << 17, n)
+        h1 = d_g1[:nx].cpu().numpy()
+        h2 = d_g2[:nx].cpu().numpy()
+        hk = rand_scalars(nx)
+        hm = (np.arange(nx, dtype=np.uint64).view(np.uint8).reshape(nx, 8).copy().reshape(-1),
+              np.arange(nx + 1, dtype=np.uint64) * 8)
+        extras["next_rows"] = {
+            "items": nx,
+            "g1_validate_per_s": world * nx / wall(lambda: eng.g1_validate_batch(h1)),
+            "g2_validate_per_s": world * nx / wall(lambda: eng.g2_validate_batch(h2)),
+            "g2_be_roundtrip_per_s": world * nx / wall(
+                lambda: eng.g2_from_be_bytes_batch(eng.g2_to_be_bytes_batch(h2), eip_mode=False)),
+            "sign_per_s": world * nx / wall(lambda: eng.sign_batch(hk, hm)),
+            "note": "host buffers, wall clock: G1Affine::new / G2Projective::new checks, big-endian codec round trip, sign",
+        }
+        ng = min(1 << 15, n)
+        hgt = d_out[:ng].cpu().numpy()
+        extras["next_rows"]["gt_mul_per_s"] = world * ng / wall(lambda: eng.gt_mul_batch(hgt, hk[:ng]))
 
     cpu = None
     if rank == 0 and world == 1:
