@@ -9,8 +9,10 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sylow_b200.h"
@@ -201,6 +203,93 @@ class Engine {
   static size_t same(size_t a, size_t b) { if (a != b) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ"); return a; }
   void ck(int st, const char* where) { if (st != 0) throw Error(st, where); }
   sylow_b200_ctx* ctx_ = nullptr;
+};
+
+// One Engine per GPU: a batch is cut into contiguous slices, one host thread drives each context, and
+// the per-item results are concatenated.  The only exchange the path has is in the product form: `verify_batch` takes
+// the 384-byte Miller partial of every GPU and finishes with 7 Fp12 products and ONE final exponentiation.
+class MultiEngine {
+ public:
+  explicit MultiEngine(const std::vector<int>& devices) {
+    if (devices.empty()) throw Error(SYLOW_B200_ERR_ARG, "MultiEngine: no devices");
+    for (int d : devices) eng_.emplace_back(new Engine(d));
+  }
+  size_t size() const { return eng_.size(); }
+  Engine& operator[](size_t i) { return *eng_[i]; }
+
+  std::vector<Gt> pairing_batch(const std::vector<G1Affine>& p, const std::vector<G2Affine>& q) {
+    if (p.size() != q.size()) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ");
+    std::vector<std::vector<Gt>> part(eng_.size());
+    run([&](size_t g, size_t lo, size_t hi) {
+      part[g] = eng_[g]->pairing_batch(slice(p, lo, hi), slice(q, lo, hi));
+    }, p.size());
+    std::vector<Gt> out;
+    out.reserve(p.size());
+    for (auto& v : part) out.insert(out.end(), v.begin(), v.end());
+    return out;
+  }
+  std::vector<G1Affine> g1_mul_batch(const std::vector<G1Affine>& pts, const std::vector<Fp>& k) {
+    if (pts.size() != k.size()) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ");
+    std::vector<std::vector<G1Affine>> part(eng_.size());
+    run([&](size_t g, size_t lo, size_t hi) { part[g] = eng_[g]->g1_mul_batch(slice(pts, lo, hi), slice(k, lo, hi)); },
+        pts.size());
+    std::vector<G1Affine> out;
+    for (auto& v : part) out.insert(out.end(), v.begin(), v.end());
+    return out;
+  }
+  // prod_i e(sig_i, G2gen) e(-H(m_i), pk_i) == 1 over all GPUs
+  bool verify_batch(const std::vector<G2Affine>& pks, const std::vector<std::string>& msgs,
+                    const std::vector<G1Affine>& sigs, const std::string& dst = DST()) {
+    if (pks.size() != msgs.size() || msgs.size() != sigs.size()) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ");
+    std::vector<std::uint8_t> partials(eng_.size() * 384);
+    run([&](size_t g, size_t lo, size_t hi) {
+      std::vector<std::uint8_t> pk((hi - lo) * 128 + 16), sg((hi - lo) * 64 + 16), buf;
+      std::vector<std::uint64_t> offs{0};
+      for (size_t i = lo; i < hi; i++) {
+        std::memcpy(&pk[128 * (i - lo)], &pks[i].x, 128);
+        std::memcpy(&sg[64 * (i - lo)], &sigs[i].x, 64);
+        buf.insert(buf.end(), msgs[i].begin(), msgs[i].end());
+        offs.push_back(buf.size());
+      }
+      if (buf.empty()) buf.push_back(0);
+      int st = sylow_b200_verify_batch_partial(eng_[g]->raw(), pk.data(), buf.data(), offs.data(), sg.data(), hi - lo,
+                                               reinterpret_cast<const std::uint8_t*>(dst.data()), dst.size(),
+                                               SYLOW_B200_HASH_KECCAK256, &partials[384 * g]);
+      if (st != 0) throw Error(st, "verify_batch_partial");
+    }, msgs.size());
+    int ok = 0;
+    int st = sylow_b200_verify_batch_finish(eng_[0]->raw(), partials.data(), eng_.size(), &ok);
+    if (st != 0) throw Error(st, "verify_batch_finish");
+    return ok != 0;
+  }
+
+ private:
+  template <class T>
+  static std::vector<T> slice(const std::vector<T>& v, size_t lo, size_t hi) {
+    return std::vector<T>(v.begin() + lo, v.begin() + hi);
+  }
+  // fn(g, lo, hi) on one thread per context over the contiguous slice [g n / G, (g + 1) n / G)
+  template <class F>
+  void run(F fn, size_t n) {
+    std::vector<std::thread> th;
+    std::vector<std::string> err(eng_.size());
+    std::vector<int> status(eng_.size(), 0);
+    for (size_t g = 0; g < eng_.size(); g++) {
+      size_t lo = g * n / eng_.size(), hi = (g + 1) * n / eng_.size();
+      th.emplace_back([&, g, lo, hi] {
+        try {
+          fn(g, lo, hi);
+        } catch (const Error& e) {
+          status[g] = e.status;
+          err[g] = e.what();
+        }
+      });
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < eng_.size(); g++)
+      if (status[g] != 0) throw Error(status[g], err[g].c_str());
+  }
+  std::vector<std::unique_ptr<Engine>> eng_;
 };
 
 }  // namespace sylow

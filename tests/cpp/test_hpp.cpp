@@ -43,6 +43,31 @@ int main() {
     Fp k = Fp::from_u64(987654321);
     Gt a = eng.pairing(eng.g1_mul_batch({g1}, {k})[0], g2), b = eng.pairing(g1, eng.g2_mul_batch({g2}, {k})[0]);
     std::printf("BILINEAR %d\n", a == b && !(a == Gt::identity()));
+    // MultiEngine: two contexts (on this box both on GPU 0) must agree with one - contiguous slices, concatenated
+    // results, and the 384-byte partial exchange of verify_batch
+    {
+      MultiEngine multi({0, 0});
+      std::vector<G1Affine> ps;
+      std::vector<G2Affine> qs;
+      std::vector<Fp> ks;
+      for (int i = 0; i < 5; i++) ks.push_back(Fp::from_u64(1000003ull * (i + 1)));
+      ps = eng.g1_mul_batch(std::vector<G1Affine>(5, g1), ks);
+      qs = eng.g2_mul_batch(std::vector<G2Affine>(5, g2), ks);
+      std::vector<Gt> one = eng.pairing_batch(ps, qs), two = multi.pairing_batch(ps, qs);
+      bool same_gt = one.size() == two.size();
+      for (size_t i = 0; i < one.size() && same_gt; i++) same_gt = one[i] == two[i];
+      std::vector<G1Affine> m1 = multi.g1_mul_batch(std::vector<G1Affine>(5, g1), ks);
+      bool same_mul = true;
+      for (size_t i = 0; i < 5; i++) same_mul = same_mul && m1[i].x == ps[i].x && m1[i].y == ps[i].y;
+      std::vector<std::string> msgs = {"a", "bb", "ccc", "dddd", "eeeee"};
+      std::vector<G1Affine> sigs = eng.sign_batch(ks, msgs);
+      std::vector<G2Affine> pks = eng.g2_mul_batch(std::vector<G2Affine>(5, g2), ks);
+      bool good = multi.verify_batch(pks, msgs, sigs);
+      std::swap(sigs[1], sigs[3]);
+      sigs[1] = sigs[0];
+      bool bad = multi.verify_batch(pks, msgs, sigs);
+      std::printf("MULTI %d %d %d %d\n", (int)same_gt, (int)same_mul, (int)good, (int)bad);
+    }
     return 0;
   } catch (const Error& e) {
     std::printf("ERROR %d %s\n", e.status, e.what());
