@@ -207,82 +207,66 @@ SY_HD void g1_store_proj(uint8_t* p, const G1Proj& q) {
   fp_store_raw(p + 32, q.y);
   fp_store_raw(p + 64, q.z);
 }
-// Projective (Montgomery form, 96 B) -> affine wire format for a whole batch with Montgomery's trick: thread t owns the
+// Projective (Montgomery form) -> affine wire format for a whole batch with Montgomery's trick: thread t owns the
 // SY_AFF_K points t, t + T, t + 2T, ... (coalesced), multiplies their Z together, inverts ONCE and unwinds.  A point at
 // infinity (Z = 0) enters the product as 1 and is written as (0, 1) + flag, like GroupAffine::from (group.rs:475-495).
+// F = Fp: G1, 96-byte projective / 64-byte affine points; F = Fp2: G2, 192 / 128 bytes.
 #define SY_AFF_K 8
-__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
-k_g1_batch_affine(const uint8_t* __restrict__ proj, size_t n, int negate, uint8_t* __restrict__ out,
-                  uint8_t* __restrict__ out_inf) {
+SY_HD Fp f_load_raw(const uint8_t* p, const Fp*) { return fp_load_raw(p); }
+SY_HD Fp2 f_load_raw(const uint8_t* p, const Fp2*) { return fp2_load_raw(p); }
+SY_HD void f_store(uint8_t* p, const Fp& v) { fp_store(p, v); }
+SY_HD void f_store(uint8_t* p, const Fp2& v) { fp2_store(p, v); }
+SY_HD Fp f_select(bool c, const Fp& a, const Fp& b) { return fp_select(c, a, b); }
+SY_HD Fp2 f_select(bool c, const Fp2& a, const Fp2& b) { return fp2_select(c, a, b); }
+template <class F>
+__device__ __forceinline__ void batch_affine(const uint8_t* __restrict__ proj, size_t n, int negate,
+                                             uint8_t* __restrict__ out, uint8_t* __restrict__ out_inf) {
+  constexpr size_t W = sizeof(F);  // bytes per coordinate in both encodings
+  const F* tag = nullptr;
+  F one;
+  f_set_one(one);
   const size_t T = (n + SY_AFF_K - 1) / SY_AFF_K;
   size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t t = t0 < T ? t0 : T - 1;  // the inversion ladder is block-synchronised: every thread runs it
-  Fp pre[SY_AFF_K];
-  Fp acc = fp_one();
+  F pre[SY_AFF_K];
+  F acc = one;
   for (int j = 0; j < SY_AFF_K; j++) {
     size_t i = t + (size_t)j * T;
-    Fp z = i < n ? fp_load_raw(proj + i * 96 + 64) : fp_one();
-    z = fp_select(fp_is_zero(z), fp_one(), z);
-    acc = fp_mul(acc, z);
+    F z = i < n ? f_load_raw(proj + i * 3 * W + 2 * W, tag) : one;
+    z = f_select(f_is_zero(z), one, z);
+    acc = f_mul(acc, z);
     pre[j] = acc;
   }
-  Fp inv = fp_inv(acc);
+  F inv = f_inv(acc);
   for (int j = SY_AFF_K - 1; j >= 0; j--) {
     size_t i = t + (size_t)j * T;
     if (i >= n) continue;  // only the last stride can be short; its z entered the product as 1
-    Fp z = fp_load_raw(proj + i * 96 + 64);
-    bool inf = fp_is_zero(z);
-    z = fp_select(inf, fp_one(), z);
-    Fp zi = j ? fp_mul(inv, pre[j - 1]) : inv;
-    inv = fp_mul(inv, z);
+    F z = f_load_raw(proj + i * 3 * W + 2 * W, tag);
+    bool inf = f_is_zero(z);
+    z = f_select(inf, one, z);
+    F zi = j ? f_mul(inv, pre[j - 1]) : inv;
+    inv = f_mul(inv, z);
     if (t0 >= T) continue;
-    Fp x = fp_mul(fp_load_raw(proj + i * 96), zi), y = fp_mul(fp_load_raw(proj + i * 96 + 32), zi);
+    F x = f_mul(f_load_raw(proj + i * 3 * W, tag), zi), y = f_mul(f_load_raw(proj + i * 3 * W + W, tag), zi);
     if (inf) {
-      x = fp_zero();
-      y = fp_one();
+      f_set_zero(x);
+      y = one;
     } else if (negate) {
-      y = fp_neg(y);
+      y = f_neg(y);
     }
-    fp_store(out + i * 64, x);
-    fp_store(out + i * 64 + 32, y);
+    f_store(out + i * 2 * W, x);
+    f_store(out + i * 2 * W + W, y);
     if (out_inf) out_inf[i] = inf;
   }
 }
-
-// the same for G2 (192-byte projective points, Z in Fp2)
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_g1_batch_affine(const uint8_t* __restrict__ proj, size_t n, int negate, uint8_t* __restrict__ out,
+                  uint8_t* __restrict__ out_inf) {
+  batch_affine<Fp>(proj, n, negate, out, out_inf);
+}
 __global__ void __launch_bounds__(SY_MUL_THREADS, 1)
 k_g2_batch_affine(const uint8_t* __restrict__ proj, size_t n, uint8_t* __restrict__ out, uint8_t* __restrict__ out_inf) {
-  const size_t T = (n + SY_AFF_K - 1) / SY_AFF_K;
-  size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t t = t0 < T ? t0 : T - 1;
-  Fp2 pre[SY_AFF_K];
-  Fp2 acc = fp2_one();
-  for (int j = 0; j < SY_AFF_K; j++) {
-    size_t i = t + (size_t)j * T;
-    Fp2 z = i < n ? fp2_load_raw(proj + i * 192 + 128) : fp2_one();
-    z = fp2_select(fp2_is_zero(z), fp2_one(), z);
-    acc = fp2_mul(acc, z);
-    pre[j] = acc;
-  }
-  Fp2 inv = fp2_inv(acc);
-  for (int j = SY_AFF_K - 1; j >= 0; j--) {
-    size_t i = t + (size_t)j * T;
-    if (i >= n) continue;
-    Fp2 z = fp2_load_raw(proj + i * 192 + 128);
-    bool inf = fp2_is_zero(z);
-    z = fp2_select(inf, fp2_one(), z);
-    Fp2 zi = j ? fp2_mul(inv, pre[j - 1]) : inv;
-    inv = fp2_mul(inv, z);
-    if (t0 >= T) continue;
-    Fp2 x = fp2_mul(fp2_load_raw(proj + i * 192), zi), y = fp2_mul(fp2_load_raw(proj + i * 192 + 64), zi);
-    if (inf) {
-      x = fp2_zero();
-      y = fp2_one();
-    }
-    fp2_store(out + i * 128, x);
-    fp2_store(out + i * 128 + 64, y);
-    if (out_inf) out_inf[i] = inf;
-  }
+  batch_affine<Fp2>(proj, n, 0, out, out_inf);
 }
 
 __global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
