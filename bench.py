@@ -399,6 +399,14 @@ def main():
             "sign_per_s": world * nx / wall(lambda: eng.sign_batch(hk, hm)),
             "note": "host buffers, wall clock: G1Affine::new / G2Projective::new checks, big-endian codec round trip, sign",
         }
+        # one large multi-scalar multiplication (bucket method) next to the same sum by ladders + tree sum
+        nm2 = min(1 << 20, n)
+        hp, hs = d_g1[:nm2].cpu().numpy(), rand_scalars(nm2)
+        t_b = wall(lambda: eng.g1_msm_bucket(hp, hs))
+        extras["next_rows"]["g1_msm_2pow%d_ms" % int(np.log2(nm2))] = {"bucket": t_b * 1e3}
+        if nm2 <= 1 << 20:
+            t_l = wall(lambda: eng.g1_sum(*eng.g1_mul_batch(hp, hs)))
+            extras["next_rows"]["g1_msm_2pow%d_ms" % int(np.log2(nm2))]["ladders"] = t_l * 1e3
         ng = min(1 << 15, n)
         hgt = d_out[:ng].cpu().numpy()
         extras["next_rows"]["gt_mul_per_s"] = world * ng / wall(lambda: eng.gt_mul_batch(hgt, hk[:ng]))

@@ -168,6 +168,13 @@ int sylow_b200_g1_sum(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const 
                       uint8_t out[64], uint8_t* out_inf);
 int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf,
                       const uint8_t* scalars /* n*32 */, size_t n, uint8_t out[64], uint8_t* out_inf);
+/* The same sum by the bucket (Pippenger) method: counting sort of the points by (window, digit), one thread per bucket,
+ * running sums per window, Horner over the windows.  window_bits = 0 chooses max(8, log2(n) - 10); buckets are cut
+ * into work items of at most 256 points, so skewed digits (equal scalars, the short top window) do not serialise.
+ * sylow_b200_g1_msm switches to it from 2^17 points on; any 256-bit scalar, infinite points are skipped. */
+int sylow_b200_g1_msm_bucket(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf,
+                             const uint8_t* scalars /* n*32 */, size_t n, int window_bits, uint8_t out[64],
+                             uint8_t* out_inf);
 
 /* Threshold-signature aggregation (examples/dkg.rs:190-226, examples/threshold_signing.rs:124-155).  A batch of
  * `n_sets` independent aggregations of `t` shares each; ids[s*t + i] is the participant id x of share i of set s

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "sylow_b200_hash_to_g1_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P]),
     "sylow_b200_g1_sum": (c_int, [_P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_g1_msm": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P]),
+    "sylow_b200_g1_msm_bucket": (c_int, [_P, _P, _P, _P, c_size_t, c_int, _P, _P]),
     "sylow_b200_lagrange_coefficients_batch": (c_int, [_P, _P, c_size_t, c_size_t, _P]),
     "sylow_b200_threshold_aggregate_batch": (c_int, [_P, _P, _P, _P, c_size_t, c_size_t, _P, _P]),
     "sylow_b200_verify_batch_same_signer": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, POINTER(c_int)]),

@@ -291,6 +291,18 @@ class Engine:
                  "g1_msm")
         return out, int(inf[0])
 
+    def g1_msm_bucket(self, pts, scalars, pts_inf=None, window_bits: int = 0):
+        """sum_i scalars[i] * pts[i] by the bucket (Pippenger) method; window_bits = 0 picks the window from n."""
+        pts = _u8(pts, 64, "pts")
+        scalars = _u8(scalars, 32, "scalars")
+        n = pts.shape[0]
+        pts_inf = None if pts_inf is None else np.ascontiguousarray(pts_inf, dtype=np.uint8).reshape(n)
+        out = np.empty(64, dtype=np.uint8)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self._lib.sylow_b200_g1_msm_bucket(self._h, _ptr(pts), _ptr(pts_inf), _ptr(scalars), n, int(window_bits),
+                                                    _ptr(out), _ptr(inf)), "g1_msm_bucket")
+        return out, int(inf[0])
+
     def lagrange_coefficients_batch(self, ids):
         """ids: (n_sets, t) participant ids -> (n_sets, t, 32) Lagrange coefficients at 0 in Fr (examples/dkg.rs:216-226)."""
         ids = np.ascontiguousarray(ids, dtype=np.uint64)

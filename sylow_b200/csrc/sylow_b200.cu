@@ -660,6 +660,148 @@ SY_HD Fp fp_final_sub_copy(Fp a) {  // p -> 0, anything below p unchanged
   fp_final_sub(a.l);
   return a;
 }
+// ---- bucket (Pippenger) multi-scalar multiplication on G1 -----------------------------------------
+// sum_i k_i P_i = sum_w 2^(c w) sum_d d * B[w][d], B[w][d] = sum of the points whose c-bit digit in window w is d.
+//   k_msm_count / k_msm_offsets / k_msm_scatter : counting sort of the point indices by (window, digit)
+//   k_msm_bucket_sum   : one thread per bucket adds its points (complete additions: repeated points and infinities
+//                        need no special case)
+//   k_msm_chunk_reduce : per window, 64 chunks of digits: local running sums S_j = sum (d - d0_j) B_d, T_j = sum B_d
+//   k_msm_window_final : R_w = sum_j S_j + d0_j T_j (small double-and-add), then Horner over the windows
+SY_HD uint32_t msm_digit(const uint8_t* scalar, int w, int c) {
+  // c <= 16 bits starting at bit w * c of a 32-byte little-endian scalar
+  int bit = w * c;
+  uint64_t v = 0;
+  for (int b = 0; b < 5; b++) {
+    int byte = (bit >> 3) + b;
+    if (byte < 32) v |= (uint64_t)scalar[byte] << (8 * b);
+  }
+  return (uint32_t)((v >> (bit & 7)) & ((1u << c) - 1u));
+}
+__global__ void k_msm_count(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ inf, size_t n, int c, int nw,
+                            uint32_t* __restrict__ count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (inf && inf[i])) return;
+  for (int w = 0; w < nw; w++) {
+    uint32_t d = msm_digit(scalars + i * 32, w, c);
+    if (d) atomicAdd(&count[((size_t)w << c) + d], 1u);
+  }
+}
+// Per window (one thread each): exclusive prefix sums of the bucket counts, and the work items of the bucket sums -
+// a bucket of `count` points is cut into ceil(count / SY_MSM_ITEM) items so that no thread adds more than SY_MSM_ITEM
+// points however skewed the digits are (the top window of 254-bit scalars has a handful of digits; equal scalars put
+// everything into one bucket).  Items of window w live at [w * max_items, ...).
+#define SY_MSM_ITEM 256
+__global__ void k_msm_offsets(const uint32_t* __restrict__ count, int c, int nw, size_t max_items,
+                              uint32_t* __restrict__ offset, uint32_t* __restrict__ cursor,
+                              uint32_t* __restrict__ item_first, uint32_t* __restrict__ item_start,
+                              uint32_t* __restrict__ item_len, uint32_t* __restrict__ items_in_window) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  uint32_t run = 0, items = 0;
+  for (uint32_t d = 0; d < (1u << c); d++) {
+    size_t k = ((size_t)w << c) + d;
+    uint32_t cnt = count[k];
+    offset[k] = run;
+    cursor[k] = run;
+    item_first[k] = items;
+    for (uint32_t j = 0; j < cnt; j += SY_MSM_ITEM) {
+      item_start[(size_t)w * max_items + items] = run + j;
+      item_len[(size_t)w * max_items + items] = cnt - j < SY_MSM_ITEM ? cnt - j : SY_MSM_ITEM;
+      items++;
+    }
+    run += cnt;
+  }
+  items_in_window[w] = items;
+}
+__global__ void k_msm_scatter(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ inf, size_t n, int c, int nw,
+                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ idx) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (inf && inf[i])) return;
+  for (int w = 0; w < nw; w++) {
+    uint32_t d = msm_digit(scalars + i * 32, w, c);
+    if (d) {
+      uint32_t pos = atomicAdd(&cursor[((size_t)w << c) + d], 1u);
+      idx[(size_t)w * n + pos] = (uint32_t)i;
+    }
+  }
+}
+SY_HD G1Proj g1_load_proj(const uint8_t* p) { return G1Proj{fp_load_raw(p), fp_load_raw(p + 32), fp_load_raw(p + 64)}; }
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_msm_item_sum(const uint8_t* __restrict__ pts, size_t n, int nw, size_t max_items,
+               const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ item_len,
+               const uint32_t* __restrict__ items_in_window, const uint32_t* __restrict__ idx,
+               uint8_t* __restrict__ item_sum) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nw * max_items) return;
+  size_t w = t / max_items;
+  if (t - w * max_items >= items_in_window[w]) return;
+  G1Proj acc = proj_zero<Fp>();
+  const uint32_t* list = idx + w * n + item_start[t];
+  for (uint32_t j = 0; j < item_len[t]; j++) {
+    const uint8_t* p = pts + (size_t)list[j] * 64;  // Montgomery form (converted once by k_fp_convert)
+    acc = proj_add(acc, G1Proj{fp_load_raw(p), fp_load_raw(p + 32), fp_one()});
+  }
+  g1_store_proj(item_sum + t * 96, acc);
+}
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_msm_bucket_sum(int c, int nw, size_t max_items, const uint32_t* __restrict__ count,
+                 const uint32_t* __restrict__ item_first, const uint8_t* __restrict__ item_sum,
+                 uint8_t* __restrict__ buckets) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ((size_t)nw << c)) return;
+  size_t w = b >> c;
+  uint32_t items = (count[b] + SY_MSM_ITEM - 1) / SY_MSM_ITEM;
+  G1Proj acc = proj_zero<Fp>();
+  for (uint32_t j = 0; j < items; j++) acc = proj_add(acc, g1_load_proj(item_sum + (w * max_items + item_first[b] + j) * 96));
+  g1_store_proj(buckets + b * 96, acc);
+}
+// small multiple m * P, m < 2^16, double-and-add from the top bit
+SY_HD G1Proj g1_mul_small(const G1Proj& p, uint32_t m) {
+  G1Proj acc = proj_zero<Fp>();
+  for (int b = 15; b >= 0; b--) {
+    acc = proj_double(acc);
+    if ((m >> b) & 1u) acc = proj_add(acc, p);
+  }
+  return acc;
+}
+#define SY_MSM_CHUNKS 64
+__global__ void __launch_bounds__(64) k_msm_chunk_reduce(const uint8_t* __restrict__ buckets, int c, int nw,
+                                                          uint8_t* __restrict__ partial) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nw * SY_MSM_CHUNKS) return;
+  int w = t / SY_MSM_CHUNKS, j = t % SY_MSM_CHUNKS;
+  uint32_t per = ((1u << c) + SY_MSM_CHUNKS - 1) / SY_MSM_CHUNKS;
+  uint32_t d0 = (uint32_t)j * per, d1 = d0 + per < (1u << c) ? d0 + per : (1u << c);
+  // digits d0 + 1 .. d1 - 1 and d1 itself belong to the next chunk's base: use the half-open range (d0, d1] mapped
+  // to local weights 1 .. d1 - d0; digit 0 never holds points, the top digit 2^c - 1 is < 2^c = last d1
+  G1Proj run = proj_zero<Fp>(), sum = proj_zero<Fp>();
+  for (uint32_t d = d1; d > d0; d--) {
+    if (d < (1u << c)) run = proj_add(run, g1_load_proj(buckets + (((size_t)w << c) + d) * 96));
+    sum = proj_add(sum, run);
+  }
+  // sum = sum_{d in (d0, d1]} (d - d0) B_d, run = sum B_d; the window value needs d B_d = (d - d0) B_d + d0 B_d
+  G1Proj r = proj_add(sum, g1_mul_small(run, d0));
+  g1_store_proj(partial + (size_t)t * 96, r);
+}
+// R_w = sum of the 64 chunk values of window w (one thread per window), written over the window's first partial
+__global__ void k_msm_window_sum(uint8_t* __restrict__ partial, int nw) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  G1Proj r = proj_zero<Fp>();
+  for (int j = 0; j < SY_MSM_CHUNKS; j++) r = proj_add(r, g1_load_proj(partial + ((size_t)w * SY_MSM_CHUNKS + j) * 96));
+  g1_store_proj(partial + (size_t)w * SY_MSM_CHUNKS * 96, r);
+}
+// Horner over the windows: ((R_{nw-1} 2^c + R_{nw-2}) 2^c + ...) - 256 doublings, the only serial part
+__global__ void k_msm_window_final(const uint8_t* __restrict__ partial, int c, int nw, uint8_t* __restrict__ out_proj) {
+  if (blockIdx.x || threadIdx.x) return;
+  G1Proj acc = proj_zero<Fp>();
+  for (int w = nw - 1; w >= 0; w--) {
+    for (int b = 0; b < c; b++) acc = proj_double(acc);
+    acc = proj_add(acc, g1_load_proj(partial + (size_t)w * SY_MSM_CHUNKS * 96));
+  }
+  g1_store_proj(out_proj, acc);
+}
+
 __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
@@ -936,7 +1078,7 @@ struct sylow_b200_ctx {
   DevBuf in_a, in_b, in_c, in_d, flag_a, flag_b, out, scratch0, scratch1, scratch2;
   int* d_fail = nullptr;
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
-  DevBuf tables, sum0, sum1, proj;
+  DevBuf tables, sum0, sum1, proj, msm;
   unsigned glued_attr_mask = 0;
 };
 
@@ -1017,6 +1159,7 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->sum0.p) cudaFree(ctx->sum0.p);
   if (ctx->sum1.p) cudaFree(ctx->sum1.p);
   if (ctx->proj.p) cudaFree(ctx->proj.p);
+  if (ctx->msm.p) cudaFree(ctx->msm.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -1993,11 +2136,89 @@ int sylow_b200_g1_sum(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pt
   return finish(ctx);
 }
 
+#define SY_MSM_BUCKET_MIN 131072
+// Bucket MSM on device buffers: d_out = 64-byte affine point, d_out_inf its flag.  window_bits = 0 picks c from n.
+static int g1_msm_bucket_dev(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_inf, const uint8_t* d_scalars,
+                             size_t n, int window_bits, uint8_t* d_out, uint8_t* d_out_inf, cudaStream_t s) {
+  int c = window_bits;
+  if (c <= 0) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    c = lg - 10 < 8 ? 8 : lg - 10;  // measured optimum (tools/msm_time.py): 8 up to 2^18 points, 10 at 2^20
+  }
+  if (c < 4) c = 4;
+  if (c > (window_bits > 0 ? 16 : 13)) c = window_bits > 0 ? 16 : 13;  // the automatic choice stops at 13 (64 digits per chunk)
+  const int nw = (256 + c - 1) / c;
+  const size_t nb = (size_t)nw << c;
+  // scratch: counts | offsets | cursors | first item (nb u32 each), item start | length (nw * max_items u32 each), items
+  // per window, index lists (nw * n u32), Montgomery points (n * 64), item sums, buckets (nb * 96), chunk partials, result
+  const size_t max_items = ((size_t)1 << c) + n / SY_MSM_ITEM + 1;
+  const size_t ni = (size_t)nw * max_items;
+  size_t o_cnt = 0, o_off = o_cnt + nb * 4, o_cur = o_off + nb * 4, o_ifi = o_cur + nb * 4, o_ist = o_ifi + nb * 4;
+  size_t o_iln = o_ist + ni * 4, o_iw = o_iln + ni * 4, o_idx = o_iw + 256;
+  size_t o_pts = (o_idx + (size_t)nw * n * 4 + 255) & ~(size_t)255, o_isum = o_pts + n * 64, o_bkt = o_isum + ni * 96;
+  size_t o_par = o_bkt + nb * 96, o_res = o_par + (size_t)nw * SY_MSM_CHUNKS * 96, total = o_res + 96;
+  CKS(reserve(ctx, ctx->msm, total));
+  uint8_t* base = ctx->msm.p;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + o_cnt);
+  uint32_t* off = reinterpret_cast<uint32_t*>(base + o_off);
+  uint32_t* cur = reinterpret_cast<uint32_t*>(base + o_cur);
+  uint32_t* ifi = reinterpret_cast<uint32_t*>(base + o_ifi);
+  uint32_t* ist = reinterpret_cast<uint32_t*>(base + o_ist);
+  uint32_t* iln = reinterpret_cast<uint32_t*>(base + o_iln);
+  uint32_t* iw = reinterpret_cast<uint32_t*>(base + o_iw);
+  uint32_t* idx = reinterpret_cast<uint32_t*>(base + o_idx);
+  CK(cudaMemsetAsync(cnt, 0, nb * 4, s));
+  k_msm_count<<<nblocks(n, 256), 256, 0, s>>>(d_scalars, d_inf, n, c, nw, cnt);
+  LAUNCHED(ctx);
+  k_msm_offsets<<<nblocks(nw, 32), 32, 0, s>>>(cnt, c, nw, max_items, off, cur, ifi, ist, iln, iw);
+  LAUNCHED(ctx);
+  k_msm_scatter<<<nblocks(n, 256), 256, 0, s>>>(d_scalars, d_inf, n, c, nw, cur, idx);
+  LAUNCHED(ctx);
+  k_fp_convert<<<nblocks(2 * n, 128), 128, 0, s>>>(d_pts, 2 * n, base + o_pts, 1);
+  LAUNCHED(ctx);
+  k_msm_item_sum<<<nblocks(ni, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(base + o_pts, n, nw, max_items, ist, iln, iw, idx,
+                                                                       base + o_isum);
+  LAUNCHED(ctx);
+  k_msm_bucket_sum<<<nblocks(nb, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(c, nw, max_items, cnt, ifi, base + o_isum,
+                                                                         base + o_bkt);
+  LAUNCHED(ctx);
+  k_msm_chunk_reduce<<<nblocks((size_t)nw * SY_MSM_CHUNKS, 64), 64, 0, s>>>(base + o_bkt, c, nw, base + o_par);
+  LAUNCHED(ctx);
+  k_msm_window_sum<<<nblocks(nw, 32), 32, 0, s>>>(base + o_par, nw);
+  LAUNCHED(ctx);
+  k_msm_window_final<<<1, 1, 0, s>>>(base + o_par, c, nw, base + o_res);
+  LAUNCHED(ctx);
+  k_g1_finish_sum<<<1, 1, 0, s>>>(base + o_res, 0, d_out, d_out_inf);
+  LAUNCHED(ctx);
+  return 0;
+}
+
+int sylow_b200_g1_msm_bucket(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars,
+                             size_t n, int window_bits, uint8_t out[64], uint8_t* out_inf) {
+  ENTER(ctx);
+  if (!out || !out_inf || (n && (!pts || !scalars)) || window_bits < 0 || window_bits > 16) return SYLOW_B200_ERR_ARG;
+  if (!n) return sylow_b200_g1_sum(ctx, nullptr, nullptr, 0, out, out_inf);
+  if (n >= ((size_t)1 << 31)) return SYLOW_B200_ERR_ARG;
+  const uint8_t *dp, *di, *dk;
+  CKS(to_dev(ctx, ctx->in_a, pts, n * 64, &dp));
+  CKS(to_dev(ctx, ctx->flag_a, pts_inf, n, &di));
+  CKS(to_dev(ctx, ctx->in_b, scalars, n * 32, &dk));
+  CKS(reserve(ctx, ctx->out, 128));
+  CKS(g1_msm_bucket_dev(ctx, dp, di, dk, n, window_bits, ctx->out.p, ctx->out.p + 64, ctx->stream));
+  CK(cudaMemcpyAsync(out, ctx->out.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_inf, ctx->out.p + 64, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
 int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars, size_t n,
                       uint8_t out[64], uint8_t* out_inf) {
   ENTER(ctx);
   if (!out || !out_inf || (n && (!pts || !scalars))) return SYLOW_B200_ERR_ARG;
   if (!n) return sylow_b200_g1_sum(ctx, nullptr, nullptr, 0, out, out_inf);
+  // from 2^17 points on the bucket method beats n GLV ladders + tree sum (tools/msm_time.py)
+  if (n >= SY_MSM_BUCKET_MIN && n < ((size_t)1 << 31))
+    return sylow_b200_g1_msm_bucket(ctx, pts, pts_inf, scalars, n, 0, out, out_inf);
   const uint8_t *dp, *di, *dk;
   CKS(to_dev(ctx, ctx->in_a, pts, n * 64, &dp));
   CKS(to_dev(ctx, ctx->flag_a, pts_inf, n, &di));

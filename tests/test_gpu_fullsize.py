@@ -171,3 +171,22 @@ def test_scalar_mul_2pow22(eng):
         assert (eng.final_exp_batch(f.reshape(1, 384))[0] == _gt_pow_gen(eng, eh)).all()
         tot += eh
     assert tot % R == e
+
+
+def test_msm_2pow18(eng):
+    """One 2^18-point multi-scalar multiplication (bucket method from 2^17 points on): with P_i = a_i G the sum
+    sum k_i P_i is (sum k_i a_i mod r) G, a single scalar multiple the oracle can check."""
+    n = 1 << 18
+    rs = np.random.RandomState(105)
+    a, k = _scalars(rs, n), _scalars(rs, n)
+    k[:5] = 0                      # zero scalars drop out
+    k[5:9] = 255                   # 2^256 - 1: reduced mod r by the group order
+    g1, _ = _gens(n)
+    P, pinf = eng.g1_mul_batch(g1, a)
+    assert not pinf.any()
+    out, inf = eng.g1_msm(P, k)
+    e = sum(x * y for x, y in zip(_ints(a), _ints(k))) % R
+    want = o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, o.G1_GEN), e))
+    assert w.b_g1(bytes(out), inf) == want
+    out2, inf2 = eng.g1_msm_bucket(P, k, window_bits=13)
+    assert w.b_g1(bytes(out2), inf2) == want

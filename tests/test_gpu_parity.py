@@ -706,3 +706,41 @@ def test_batched_affine_conversion(eng):
     hs = np.concatenate([eng.hash_to_g1_batch(msgs[s:s + 8192])[0] for s in range(0, n, 8192)])
     assert (h == hs).all() and not hinf.any()
     assert w.b_g1(bytes(h[n - 1])) == o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(msgs[n - 1]))
+
+
+def test_bucket_msm(eng):
+    """Pippenger MSM against the oracle's sum of scalar multiples for several window sizes, with zero and
+    oversize scalars, repeated points and infinite points, and against the ladder path at 20 000 points."""
+    rng = random.Random(35)
+    n = 150
+    base = [w.rand_g1(rng) for _ in range(12)]
+    pts = [rng.choice(base) for _ in range(n)]
+    ks = [rng.randrange(1 << 256) for _ in range(n)]
+    ks[0], ks[1], ks[2], ks[3] = 0, 1, o.R_ORDER, (1 << 256) - 1
+    inf = np.zeros(n, np.uint8)
+    inf[[5, 17]] = 1
+    acc = o.proj_zero(o.FpOps)
+    for i, (p, k) in enumerate(zip(pts, ks)):
+        if not inf[i]:
+            acc = o.proj_add(o.FpOps, acc, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k % o.R_ORDER))
+    ref = o.proj_to_affine(o.FpOps, acc)
+    P, K = arr([w.g1_b(p) for p in pts]), arr([w.fp_b(k) for k in ks])
+    for c in (4, 5, 7, 11, 16, 0):
+        out, oinf = eng.g1_msm_bucket(P, K, pts_inf=inf, window_bits=c)
+        assert w.b_g1(bytes(out), oinf) == ref, c
+    # everything cancels: k P + (r - k) P = infinity
+    out, oinf = eng.g1_msm_bucket(arr([w.g1_b(base[0])] * 2), arr([w.fp_b(7), w.fp_b(o.R_ORDER - 7)]), window_bits=6)
+    assert oinf == 1 and w.b_g1(bytes(out), 1) == (0, 1, True)
+    # 20 000 points: the ladders + tree sum (what sylow_b200_g1_msm uses below 2^17 points) must give the same point
+    rs = np.random.RandomState(36)
+    m = 20000
+    k2 = rs.randint(0, 256, size=(m, 32), dtype=np.uint8)
+    seeds, _ = eng.g1_mul_batch(np.repeat(arr([w.g1_b(o.G1_GEN)]), 256, axis=0), k2[:256])
+    P2 = np.tile(seeds, (m // 256 + 1, 1))[:m].copy()
+    prods, pinf = eng.g1_mul_batch(P2, k2)
+    want = eng.g1_sum(prods, pts_inf=pinf)
+    assert (eng.g1_msm(P2, k2)[0] == want[0]).all() and (eng.g1_msm_bucket(P2, k2, window_bits=9)[0] == want[0]).all()
+    # maximal skew: every scalar equal, so one bucket per window holds all 20 000 points (cut into bounded work items)
+    ones = np.zeros((m, 32), np.uint8)
+    ones[:, 0] = 1
+    assert (eng.g1_msm_bucket(P2, ones)[0] == eng.g1_sum(P2)[0]).all()
