@@ -95,13 +95,30 @@ SY_HD_ADD Fp2 fp2_sub_mul_xi(const Fp2& t, const Fp2& a) {
 //   c0 = a0 b0 - a1 b1            in (-p^2, p^2): add p*R when negative, then < p*R
 //   c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 = a0 b1 + a1 b0   in [0, 2 p^2) subset [0, p*R)
 // The sums a0+a1, b0+b1 are NOT reduced (< 2p < 2^255, product < 4 p^2 < 2^510).
+// ptxas interleaves every independent carry chain it can find; with three products and two reductions in one
+// function it runs out of the seven predicate registers that hold the carries and spills them into a bit mask
+// (about 50 LOP3 set/test instructions per Fp2 product).  Two chains per warp already saturate the multiplier
+// pipe, so the products and the reductions are ordered by empty asm statements that make the next one's first
+// operand depend on the previous one's last limb.
+#ifndef SY_CHAIN_FENCE
+#define SY_CHAIN_FENCE 1
+#endif
+#if SY_CHAIN_FENCE && defined(__CUDA_ARCH__)
+#define SY_AFTER(x, y) asm volatile("" : "+r"(x) : "r"(y))
+#else
+#define SY_AFTER(x, y) ((void)0)
+#endif
 SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
 #if SY_LAZY_FP2
-  uint32_t t0[16], t1[16], t2[16], sa[8], sb[8];
+  uint32_t t0[16], t1[16], t2[16], sa[8], sb[8], a1[8];
   fp_mul_wide(t0, a.c0.l, b.c0.l);
-  fp_mul_wide(t1, a.c1.l, b.c1.l);
-  fp_add_nr(sa, a.c0.l, a.c1.l);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a1[i] = a.c1.l[i];
+  SY_AFTER(a1[0], t0[15]);
+  fp_mul_wide(t1, a1, b.c1.l);
+  fp_add_nr(sa, a.c0.l, a1);
   fp_add_nr(sb, b.c0.l, b.c1.l);
+  SY_AFTER(sa[0], t1[15]);
   fp_mul_wide(t2, sa, sb);
   wide_sub(t2, t0);
   wide_sub(t2, t1);
@@ -109,6 +126,7 @@ SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
   wide_add_pR(t0, neg);
   Fp2 r;
   r.c0 = fp_redc_wide(t0);
+  SY_AFTER(t2[0], r.c0.l[7]);
   r.c1 = fp_redc_wide(t2);
   return r;
 #else
