@@ -50,10 +50,10 @@ SY_HD_NOINLINE Ell g2_addition_step(G2Proj& r, const Fp2& qx, const Fp2& qy) {
 }
 
 // f <- f * l(P),  l(P) = (c0, c1 * yP, c2 * xP)   (pairing.rs:597)
-SY_HD Fp12 miller_mul_line(const Fp12& f, const Ell& l, const Fp& xp, const Fp& yp) {
+SY_HD void miller_mul_line(Fp12& f, const Ell& l, const Fp& xp, const Fp& yp) {
   Fp2 lvw = fp2_mul_fp(l.c1, yp);
   Fp2 lvv = fp2_mul_fp(l.c2, xp);
-  return fp12_sparse_mul(f, l.c0, lvw, lvv);
+  fp12_sparse_mul_assign(f, l.c0, lvw, lvv);
 }
 
 // Fused precompute + miller_loop for one (P, Q) pair of finite affine points.
@@ -65,15 +65,15 @@ SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const
     SY_LOOP_SYNC();
     Ell l = g2_doubling_step(r);
     SY_STEP_SYNC();
-    if (i != 0) f = fp12_sqr(f);  // 1^2 = 1
+    if (i != 0) fp12_sqr_assign(f);  // 1^2 = 1
     SY_STEP_SYNC();
-    f = miller_mul_line(f, l, xp, yp);
+    miller_mul_line(f, l, xp, yp);
     int digit = SY_TAB(kAteNaf)[i];
     if (digit != 0) {
       SY_STEP_SYNC();
       l = g2_addition_step(r, qx, digit > 0 ? qy : nqy);
       SY_STEP_SYNC();
-      f = miller_mul_line(f, l, xp, yp);
+      miller_mul_line(f, l, xp, yp);
     }
   }
   // Q1 = psi(Q), Q2 = -psi(Q1)   (pairing.rs:701-706, g2.rs:140-152)
@@ -82,9 +82,9 @@ SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const
   Fp2 q2x = fp2_mul(SY_TAB(kEpsExp0)[0], fp2_conj(q1x));
   Fp2 q2y = fp2_neg(fp2_mul(SY_TAB(kEpsExp1)[0], fp2_conj(q1y)));
   Ell l = g2_addition_step(r, q1x, q1y);
-  f = miller_mul_line(f, l, xp, yp);
+  miller_mul_line(f, l, xp, yp);
   l = g2_addition_step(r, q2x, q2y);
-  f = miller_mul_line(f, l, xp, yp);
+  miller_mul_line(f, l, xp, yp);
   return f;
 }
 
@@ -113,11 +113,11 @@ struct MillerG1 {
   Fp x, y;
   bool skip;
 };
-SY_HD Fp12 glued_mul_line(const Fp12& f, const Ell& l, const MillerG1& p) {
+SY_HD void glued_mul_line(Fp12& f, const Ell& l, const MillerG1& p) {
   Fp2 l0 = fp2_select(p.skip, fp2_one(), l.c0);
   Fp2 lvw = fp2_select(p.skip, fp2_zero(), fp2_mul_fp(l.c1, p.y));
   Fp2 lvv = fp2_select(p.skip, fp2_zero(), fp2_mul_fp(l.c2, p.x));
-  return fp12_sparse_mul(f, l0, lvw, lvv);
+  fp12_sparse_mul_assign(f, l0, lvw, lvv);
 }
 
 // glued_miller_loop (pairing.rs:970-1022) for NV pairs whose G2 point is per-item (line coefficients
@@ -138,20 +138,20 @@ SY_HD_NOINLINE Fp12 glued_miller_loop(const MillerG1* p /* NV + NF */, const Fp2
   int idx = 0;
   for (int i = 0; i < 64; i++) {
     SY_LOOP_SYNC();
-    if (i != 0) f = fp12_sqr(f);
+    if (i != 0) fp12_sqr_assign(f);
     for (int v = 0; v < NV; v++) {
       Ell l = g2_doubling_step(r[v]);
-      f = glued_mul_line(f, l, p[v]);
+      glued_mul_line(f, l, p[v]);
     }
-    for (int t = 0; t < NF; t++) f = glued_mul_line(f, tables[t][idx], p[NV + t]);
+    for (int t = 0; t < NF; t++) glued_mul_line(f, tables[t][idx], p[NV + t]);
     idx++;
     int digit = SY_TAB(kAteNaf)[i];
     if (digit != 0) {
       for (int v = 0; v < NV; v++) {
         Ell l = g2_addition_step(r[v], qx[v], digit > 0 ? qy[v] : nqy[v]);
-        f = glued_mul_line(f, l, p[v]);
+        glued_mul_line(f, l, p[v]);
       }
-      for (int t = 0; t < NF; t++) f = glued_mul_line(f, tables[t][idx], p[NV + t]);
+      for (int t = 0; t < NF; t++) glued_mul_line(f, tables[t][idx], p[NV + t]);
       idx++;
     }
   }
@@ -167,9 +167,9 @@ SY_HD_NOINLINE Fp12 glued_miller_loop(const MillerG1* p /* NV + NF */, const Fp2
         q1y = ty;
       }
       Ell l = g2_addition_step(r[v], q1x, q1y);
-      f = glued_mul_line(f, l, p[v]);
+      glued_mul_line(f, l, p[v]);
     }
-    for (int t = 0; t < NF; t++) f = glued_mul_line(f, tables[t][idx], p[NV + t]);
+    for (int t = 0; t < NF; t++) glued_mul_line(f, tables[t][idx], p[NV + t]);
     idx++;
   }
   return f;
@@ -199,7 +199,7 @@ SY_HD void fp4_square(const Fp2& a, const Fp2& b, Fp2& c0, Fp2& c1) {
 }
 
 // Granger-Scott (pairing.rs:309-346)
-SY_HD_NOINLINE Fp12 cyclotomic_squared(const Fp12& f) {
+SY_HD_NOINLINE void cyclotomic_square_assign(Fp12& f) {
   Fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
   Fp2 t0, t1, t2, t3;
   fp4_square(z0, z1, t0, t1);
@@ -218,7 +218,12 @@ SY_HD_NOINLINE Fp12 cyclotomic_squared(const Fp12& f) {
   z2 = fp2_add(fp2_dbl(z2), t0);
   z3 = fp2_sub(t2, z3);
   z3 = fp2_add(fp2_dbl(z3), t2);
-  return Fp12{Fp6{z0, z4, z3}, Fp6{z2, z1, z5}};
+  f = Fp12{Fp6{z0, z4, z3}, Fp6{z2, z1, z5}};
+}
+SY_HD Fp12 cyclotomic_squared(const Fp12& f) {
+  Fp12 r = f;
+  cyclotomic_square_assign(r);
+  return r;
 }
 
 // conj(f^x) with x = BLS_X (pairing.rs:366-392).  The reference walks 256 exponent bits one at a time; the
@@ -227,15 +232,15 @@ SY_HD_NOINLINE Fp12 cyclotomic_squared(const Fp12& f) {
 // digits multiply by the conjugate, which is the inverse on the cyclotomic subgroup f lives in.
 SY_HD_NOINLINE Fp12 exp_by_neg_z(const Fp12& f) {
   Fp12 f3 = fp12_mul(cyclotomic_squared(f), f);
+  const Fp12 fc = fp12_conj(f), f3c = fp12_conj(f3);  // the negative digits' factors, conjugated once
   Fp12 res = SY_TAB(kXWnaf3)[0] == 3 ? f3 : f;
   for (int i = 1; i < SY_XWNAF3_LEN; i++) {
     SY_LOOP_SYNC();
-    res = cyclotomic_squared(res);
+    cyclotomic_square_assign(res);
     int d = SY_TAB(kXWnaf3)[i];
     if (d != 0) {
       SY_STEP_SYNC();
-      const Fp12& t = (d == 3 || d == -3) ? f3 : f;
-      res = fp12_mul(res, d > 0 ? t : fp12_conj(t));
+      fp12_mul_assign(res, d == 3 ? f3 : d == -3 ? f3c : d == 1 ? f : fc);
     }
   }
   return fp12_conj(res);
@@ -297,15 +302,16 @@ SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
   for (int w = 16; w >= 0; w--) {
     SY_LOOP_SYNC();
     if (w != 16) {
-      acc = cyclotomic_squared(acc);
-      acc = cyclotomic_squared(acc);
-      acc = cyclotomic_squared(acc);
-      acc = cyclotomic_squared(acc);
+      cyclotomic_square_assign(acc);
+      cyclotomic_square_assign(acc);
+      cyclotomic_square_assign(acc);
+      cyclotomic_square_assign(acc);
     }
     for (int e = 0; e < 4; e++) {
       Fp12 t = tab[(mag[e][w >> 3] >> ((w & 7) * 4)) & 15u];
       if (e) t = fp12_frobenius(t, e);
-      acc = fp12_mul(acc, neg[e] ? fp12_conj(t) : t);
+      if (neg[e]) t = fp12_conj(t);
+      fp12_mul_assign(acc, t);
     }
   }
   return acc;
@@ -313,12 +319,12 @@ SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
   Fp12 acc = tab[k[7] >> 28];
   for (int w = 62; w >= 0; w--) {
     SY_LOOP_SYNC();
-    acc = cyclotomic_squared(acc);
-    acc = cyclotomic_squared(acc);
-    acc = cyclotomic_squared(acc);
-    acc = cyclotomic_squared(acc);
+    cyclotomic_square_assign(acc);
+    cyclotomic_square_assign(acc);
+    cyclotomic_square_assign(acc);
+    cyclotomic_square_assign(acc);
     uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
-    acc = fp12_mul(acc, tab[d]);
+    fp12_mul_assign(acc, tab[d]);
   }
   return acc;
 #endif
