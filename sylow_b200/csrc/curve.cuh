@@ -364,13 +364,25 @@ SY_HD bool g2_proj_eq(const G2Proj& a, const G2Proj& b) {
   bool same = fp2_eq(fp2_mul(a.x, b.z), fp2_mul(b.x, a.z)) & fp2_eq(fp2_mul(a.y, b.z), fp2_mul(b.y, a.z));
   return (az & bz) | (!az & !bz & same);
 }
-// [x]Q for the BN parameter x (63 bits, compile-time constant: uniform control flow)
+// [x]Q for the BN parameter x (63 bits, compile-time constant: uniform control flow), width-4 NAF: the odd
+// multiples Q, 3Q, 5Q, 7Q and 13 additions instead of the 27 of the binary expansion
 SY_HD_NOINLINE G2Proj g2_mul_by_x(const G2Proj& q) {
-  G2Proj acc = q;
-  for (int i = 61; i >= 0; i--) {
+  G2Proj tab[4];
+  {
+    G2Proj q2 = proj_double(q);
+    tab[0] = q;
+    for (int i = 1; i < 4; i++) tab[i] = proj_add(tab[i - 1], q2);
+  }
+  G2Proj acc = tab[(SY_TAB(kXWnaf4)[0] - 1) >> 1];
+  for (int i = 1; i < SY_XWNAF4_LEN; i++) {
     SY_LOOP_SYNC();
     acc = proj_double(acc);
-    if ((SY_BLS_X >> i) & 1) acc = proj_add(acc, q);
+    int d = SY_TAB(kXWnaf4)[i];
+    if (d != 0) {
+      G2Proj t = tab[((d > 0 ? d : -d) - 1) >> 1];
+      if (d < 0) t.y = fp2_neg(t.y);
+      acc = proj_add(acc, t);
+    }
   }
   return acc;
 }
