@@ -32,13 +32,13 @@ using namespace sylow;
 #define SY_SCALAR_MUL proj_scalar_mul
 #endif
 #ifndef SY_MILLER_THREADS
-#define SY_MILLER_THREADS 256
+#define SY_MILLER_THREADS 128
 #endif
 #ifndef SY_MILLER_MINB
-#define SY_MILLER_MINB 1
+#define SY_MILLER_MINB 2
 #endif
 #ifndef SY_FEXP_THREADS
-#define SY_FEXP_THREADS 256
+#define SY_FEXP_THREADS 384
 #endif
 #ifndef SY_FEXP_MINB
 #define SY_FEXP_MINB 1
@@ -1521,9 +1521,12 @@ static int finish(sylow_b200_ctx* ctx) {
   if (!(ctx)) return SYLOW_B200_ERR_ARG;          \
   CK(cudaSetDevice((ctx)->device));
 
-// Host-pointer pairing / Miller-loop batch.  Large batches are cut into chunks of four full waves (SMs x 256 threads
-// x 4) and pipelined over three streams: the host->device copy of chunk c+1 and the device->host copy of chunk c-1
-// run under the kernels of chunk c, so the PCIe time of the 576 bytes per pairing disappears from the call.
+// Host-pointer pairing / Miller-loop batch.  Large batches are cut into chunks of whole waves of both kernels (SMs x
+// 1536 pairs: six Miller-loop waves, four final-exponentiation waves) and pipelined over three streams: the
+// host->device copy of chunk c+1 and the device->host copy of chunk c-1 run under the kernels of chunk c, so the
+// PCIe time of the 576 bytes per pairing disappears from the call.
+static constexpr size_t sy_gcd(size_t a, size_t b) { return b ? sy_gcd(b, a % b) : a; }
+static constexpr size_t sy_lcm(size_t a, size_t b) { return a / sy_gcd(a, b) * b; }
 static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                         const uint8_t* g2_inf, size_t n, uint8_t* out, bool final_exp) {
   const uint8_t *d1i, *d2i;
@@ -1533,7 +1536,8 @@ static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g
   CKS(to_dev(ctx, ctx->flag_a, g1_inf, n, &d1i));
   CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
   if (d1i || d2i) CK(cudaStreamSynchronize(ctx->stream));  // the flags are read from both compute streams
-  const size_t chunk = (size_t)ctx->sms * SY_MILLER_THREADS * 4;
+  // whole waves of both kernels: a multiple of the threads each of them keeps resident per SM
+  const size_t chunk = (size_t)ctx->sms * sy_lcm(SY_MILLER_THREADS * SY_MILLER_MINB, SY_FEXP_THREADS * SY_FEXP_MINB) * 2;
   const size_t n_chunks = n <= 2 * chunk ? 1 : (n + chunk - 1) / chunk;
   const size_t step = n_chunks == 1 ? n : chunk;
   std::vector<cudaEvent_t> ev(2 * n_chunks, nullptr);

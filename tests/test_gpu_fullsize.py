@@ -56,9 +56,9 @@ def test_pairing_batch_2pow20(eng):
     P, pinf = eng.g1_mul_batch(g1, a)
     Q, qinf = eng.g2_mul_batch(g2, b)
     assert not pinf.any() and not qinf.any()
-    # a few infinite inputs on both sides of the host path's chunk boundaries (4 waves = SMs * 1024 pairs per chunk):
+    # a few infinite inputs on both sides of the host path's chunk boundaries (whole waves of both kernels = SMs * 1536 pairs per chunk):
     # pairing(inf, .) = pairing(., inf) = identity (pairing.rs:876-886)
-    chunk = torch.cuda.get_device_properties(0).multi_processor_count * 1024
+    chunk = torch.cuda.get_device_properties(0).multi_processor_count * 1536
     holes = [chunk - 1, chunk, 3 * chunk + 5, n - 1]
     pinf[holes[:2]] = 1
     qinf[holes[2:]] = 1
