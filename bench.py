@@ -27,10 +27,10 @@ LIMB_PRODUCTS_PER_FP_MUL = 136        # 8-limb CIOS: 64 (a*b) + 64 (m*p) + 8 (m)
 FP_MUL_MILLER_FUSED = 8444            # fused Miller loop, per pair                     SURVEY.md 8(d)
 FP_MUL_FINAL_EXP = 8822 + 380         # final exponentiation + one Fermat inversion     SURVEY.md 8(d)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_miller launch at 2^20 pairs, from the committed
-# `ncu --set full` capture profiles/r01i_k_miller_2pow20.json (local-memory frame spill traffic; the
+# `ncu --set full` capture profiles/r01l_k_miller_2pow20.json (local-memory frame spill traffic; the
 # algorithmic bytes are 576 B per pairing: this kernel is bound by the integer-multiply pipe, not by HBM - the
-# 89 GB are write-backs of the 2.8 KB/thread frame from L2, 488 GB/s or 7 % of the measured HBM bandwidth).
-NCU_DRAM_BYTES_K_MILLER_2POW20 = 89.0e9
+# 89 GB are write-backs of the 2.8 KB/thread frame from L2, 506 GB/s or 8 % of the measured HBM bandwidth).
+NCU_DRAM_BYTES_K_MILLER_2POW20 = 89.1e9
 
 
 def parse():
@@ -434,13 +434,13 @@ def main():
                          "unit": "T limb-products/s (32x32->64 multiply-adds)",
                          "frac": lp_miller / peak_limb_products,
                          "traffic": NCU_DRAM_BYTES_K_MILLER_2POW20 if args.log2n == 20 else None,
-                         "traffic_note": "bytes per k_miller launch from profiles/r01i (ncu --set full); algorithmic "
+                         "traffic_note": "bytes per k_miller launch from profiles/r01l (ncu --set full); algorithmic "
                                          "bytes per launch = n * 576",
                          "peak_source": "measured live: IMAD.WIDE.U32.X carry-chain probe on all SMs",
                          "ms_per_launch": ms_miller,
-                         "ncu_fmaheavy_pipe_pct": 66.8 if args.log2n == 20 else None,
+                         "ncu_fmaheavy_pipe_pct": 69.2 if args.log2n == 20 else None,
                          "ncu_note": "sm__pipe_fmaheavy_cycles_active of one k_miller launch at 2^20 pairs, "
-                                     "profiles/r01i_k_miller_2pow20.json",
+                                     "profiles/r01l_k_miller_2pow20.json",
                          "hbm_gbs_load_store": n * (192 + 384) / (ms_miller * 1e-3) / 1e9,
                          "final_exp": {"ms_per_launch": ms_fexp, "achieved": lp_fexp / 1e12,
                                        "frac": lp_fexp / peak_limb_products}},
