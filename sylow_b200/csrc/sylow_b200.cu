@@ -44,6 +44,12 @@ using namespace sylow;
 #define SY_FEXP_MINB 1
 #endif
 #define SY_MUL_THREADS 256
+#ifndef SY_G2_THREADS
+#define SY_G2_THREADS 256
+#endif
+#ifndef SY_G2_MINB
+#define SY_G2_MINB 2
+#endif
 #define SY_HASH_THREADS 256
 #ifndef SY_G1_MINB
 #define SY_G1_MINB 2  // resident 256-thread blocks per SM for the Fp-only kernels (G1 ladder, hash-to-curve)
@@ -289,7 +295,7 @@ k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
   if (out_inf) out_inf[i] = r.inf;
 }
 
-__global__ void __launch_bounds__(SY_MUL_THREADS, 1)
+__global__ void __launch_bounds__(SY_G2_THREADS, SY_G2_MINB)
 k_g2_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
                        const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out,
                        uint8_t* __restrict__ out_inf, uint8_t* __restrict__ proj_out) {
@@ -1311,7 +1317,7 @@ int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const u
     CKS(reserve(ctx, ctx->proj, n * 192));
     proj = ctx->proj.p;
   }
-  k_g2_mul<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, pick(ctx, stream)>>>(pts, pts_inf, scalars,
+  k_g2_mul<<<nblocks(n, SY_G2_THREADS), SY_G2_THREADS, 0, pick(ctx, stream)>>>(pts, pts_inf, scalars,
                                                                                           n, out, out_inf, proj);
   LAUNCHED(ctx);
   if (proj) {
