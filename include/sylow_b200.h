@@ -15,14 +15,24 @@
  *   infinity  parallel uint8 flag array (mirrors `infinity: Choice`); NULL = no point is infinite.
  *
  * Conventions: return 0 on success, a negative sylow_b200_status otherwise; never aborts; no
- * callee-allocated memory is returned; a context is used by one call at a time and is bound to ONE
- * CUDA device (one process or thread per GPU; shard batches as contiguous slices and combine the
- * 384-byte Miller partial products with sylow_b200_fp12_product).  Host-pointer entry
+ * callee-allocated memory is returned; a context is used by one call at a time.  A context made by
+ * sylow_b200_create is bound to ONE CUDA device; one made by sylow_b200_create_multi owns one such
+ * context per listed device and shards every batched host-pointer call as contiguous slices, one host
+ * thread per GPU, combining the 384-byte Miller partial products of the product forms on the first
+ * device - results are bit-identical to the single-device call.  (One process per GPU
+ * works too: shard the batch yourself and combine partials with sylow_b200_fp12_product /
+ * sylow_b200_verify_batch_finish; bench.py does that over torch.distributed.)  Host-pointer entry
  * points are synchronous (results are in host memory on return).  The `_dev` entry points take
- * DEVICE pointers (16-byte aligned) and enqueue on `stream` (a cudaStream_t passed as void*; NULL =
- * the context's own stream) without synchronising - this is what bench.py times with inputs resident
- * in HBM.  There is no CPU fallback: every entry point fails with SYLOW_B200_ERR_CUDA if no device
- * is usable.
+ * DEVICE pointers (16-byte aligned) of a single-device context and enqueue on `stream` (a
+ * cudaStream_t passed as void*; NULL = the context's own stream) without synchronising - this is what
+ * bench.py times with inputs resident in HBM.  All `_dev` calls on one context share its scratch
+ * buffers: enqueue them on ONE stream (or order the streams yourself); the library does not
+ * serialise calls issued on different streams.  There is no CPU fallback: every entry point fails
+ * with SYLOW_B200_ERR_CUDA if no device is usable.
+ *
+ * Points are NOT validated by the pairing / BLS entry points (sylow's typed API cannot hold an invalid
+ * point; raw bytes can): run sylow_b200_g1_validate_batch / sylow_b200_g2_validate_batch on untrusted
+ * input first.  An off-curve or off-subgroup input gives an unspecified (but memory-safe) result.
  */
 #ifndef SYLOW_B200_H
 #define SYLOW_B200_H
@@ -51,8 +61,16 @@ typedef enum {
 #define SYLOW_B200_HASH_SHA256 1      /* XMDExpander::<Sha256>, the digest of the reference's RFC 9380 vectors */
 #define SYLOW_B200_HASH_SHAKE128 2    /* XOFExpander::<Shake128> (hasher.rs:258-330), security parameter k = 128 */
 
-/* Context: owns one stream and growable device/pinned staging buffers on `device_id`. */
+/* Context: owns its streams and growable device staging buffers on `device_id`. */
 int sylow_b200_create(sylow_b200_ctx** out, int device_id);
+/* Multi-device context over device_ids[0 .. n_devices): every batched host-pointer entry point shards
+ * its batch over the devices; entry points without a sharded form run on device_ids[0].  The same device may be
+ * listed more than once (two slices then share that GPU). */
+int sylow_b200_create_multi(sylow_b200_ctx** out, const int* device_ids, int n_devices);
+/* Number of devices of a context (1 for sylow_b200_create) and the single-device context of device slot i, which the
+ * `_dev` entry points need (owned by the parent: do not destroy it). */
+int sylow_b200_device_count(const sylow_b200_ctx* ctx);
+sylow_b200_ctx* sylow_b200_device_ctx(sylow_b200_ctx* ctx, int i);
 int sylow_b200_destroy(sylow_b200_ctx* ctx);
 const char* sylow_b200_strerror(int status);
 /* cudaError_t of the last failing CUDA call on this context (0 if none). */
@@ -163,7 +181,7 @@ int sylow_b200_gt_mul_batch(sylow_b200_ctx* ctx, const uint8_t* gt /* n*384 */, 
 
 /* out = sum_i pts[i] (affine + infinity flag): signature aggregation.  sylow_b200_g1_msm = sum_i scalars[i] * pts[i]
  * (Lagrange-weighted aggregation of examples/dkg.rs:190-236) as a batch of ladders plus the same tree sum - a
- * straightforward MSM, not a bucket method. */
+ * batch of GLV ladders plus the same tree sum below 2^17 points, the bucket method (sylow_b200_g1_msm_bucket) above. */
 int sylow_b200_g1_sum(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf, size_t n,
                       uint8_t out[64], uint8_t* out_inf);
 int sylow_b200_g1_msm(sylow_b200_ctx* ctx, const uint8_t* pts /* n*64 */, const uint8_t* pts_inf,
@@ -207,38 +225,52 @@ int sylow_b200_expand_message_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, co
 int sylow_b200_hash_to_field_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
                                    const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out /* n*64 */);
 
-/* sigs[i] = affine(sign(sk[i], msg_i)) = sk[i] * H(msg_i)   (lib.rs:179-187). */
+/* sigs[i] = affine(sign(sk[i], msg_i)) = sk[i] * H(msg_i)   (lib.rs:179-187).  sigs_out_inf (may be NULL) flags the
+ * identity, which sk = 0 mod r produces. */
 int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks /* n*32 */, const uint8_t* msgs,
                           const uint64_t* offsets, size_t n, const uint8_t* dst, size_t dst_len, int hash_id,
-                          uint8_t* sigs_out /* n*64 */);
+                          uint8_t* sigs_out /* n*64 */, uint8_t* sigs_out_inf /* n, may be NULL */);
 
 /* ok_out[i] = verify(pk[i], msg_i, sig[i]) = (e(sig, G2gen) == e(H(msg), pk))  (lib.rs:223-236),
- * one boolean per signature. */
-int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks /* n*128 */, const uint8_t* msgs,
-                           const uint64_t* offsets, const uint8_t* sigs /* n*64 */, size_t n, const uint8_t* dst,
-                           size_t dst_len, int hash_id, uint8_t* ok_out);
+ * one boolean per signature.  pks_inf / sigs_inf (may be NULL) flag identity keys / signatures: that side's pairing
+ * is Gt::identity(), as in pairing() (pairing.rs:876-886). */
+int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks /* n*128 */, const uint8_t* pks_inf,
+                           const uint8_t* msgs, const uint64_t* offsets, const uint8_t* sigs /* n*64 */,
+                           const uint8_t* sigs_inf, size_t n, const uint8_t* dst, size_t dst_len, int hash_id,
+                           uint8_t* ok_out);
 
-/* f_out = miller(sum_i sig_i, G2gen) * prod_i miller(-H(msg_i), pk_i): this GPU's 384-byte share of the batch check of
- * examples/verify_multiple_messages_same_signer.rs:40-60.  (prod_i e(sig_i, G2gen) = e(sum_i sig_i, G2gen), so the
- * product of all shares has the same final exponentiation as the reference's 2n-pair glued loop.) */
-int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs,
-                                    const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
-                                    size_t dst_len, int hash_id, uint8_t f_out[384]);
+/* The product check of examples/verify_multiple_messages_same_signer.rs:40-60 over n (key, message, signature)
+ * triples:   prod_i e(r_i sig_i, G2gen) e(-r_i H(msg_i), pk_i) == 1.
+ *   weight_seed == NULL: r_i = 1, exactly the reference example.  This is AGGREGATE verification: it proves the
+ *     product, not each factor - errors that cancel (sig_1 + D, sig_2 - D) pass.  Use it when the signatures come
+ *     from one aggregator, or use sylow_b200_verify_each for per-signature verdicts.
+ *   weight_seed != NULL (32 secret random bytes drawn AFTER the batch is fixed): BATCH verification with
+ *     r_i = the first 8 bytes of Keccak-256(seed || LE64(first_index + i)) | 1; a batch with any invalid signature
+ *     passes with probability <= 2^-63.  Costs two 64-bit G1 ladders per signature on top.
+ * _partial: this GPU's 384-byte share f_out = miller(sum_i r_i sig_i, G2gen) * prod_i miller(-r_i H(msg_i), pk_i)
+ *   (prod_i e(sig_i, G2gen) = e(sum_i sig_i, G2gen), so the product of all shares has the same final exponentiation
+ *   as the reference's 2n-pair glued loop); first_index = global index of the slice's first triple.
+ * _finish: *ok = (final_exponentiation(prod_i partials[i]) == Gt::identity()).  n_partials = number of GPUs.
+ * sylow_b200_verify_batch = partial + finish (on a multi-device context: one partial per GPU). */
+int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* pks_inf, const uint8_t* msgs,
+                                    const uint64_t* offsets, const uint8_t* sigs, const uint8_t* sigs_inf, size_t n,
+                                    const uint8_t* dst, size_t dst_len, int hash_id,
+                                    const uint8_t* weight_seed /* 32 B or NULL */, uint64_t first_index,
+                                    uint8_t f_out[384]);
+int sylow_b200_verify_batch_finish(sylow_b200_ctx* ctx, const uint8_t* partials /* n_partials*384 */,
+                                   size_t n_partials, int* ok);
+int sylow_b200_verify_batch(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* pks_inf, const uint8_t* msgs,
+                            const uint64_t* offsets, const uint8_t* sigs, const uint8_t* sigs_inf, size_t n,
+                            const uint8_t* dst, size_t dst_len, int hash_id,
+                            const uint8_t* weight_seed /* 32 B or NULL */, int* ok);
 
 /* The reference example's exact setting - many messages, ONE signer (examples/verify_multiple_messages_same_signer.rs:
  * 40-60): prod e(sig_i, G2gen) e(-H(m_i), pk) = e(sum sig_i, G2gen) e(-sum H(m_i), pk), i.e. n hashes, 2n point
- * additions and two Miller loops for the whole batch.  Same verdict as the product form. */
-int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk /* 128 */, const uint8_t* msgs,
-                                        const uint64_t* offsets, const uint8_t* sigs /* n*64 */, size_t n,
-                                        const uint8_t* dst, size_t dst_len, int hash_id, int* ok);
-
-/* *ok = (final_exponentiation(prod_i partials[i]) == Gt::identity()).  n_partials = number of GPUs. */
-int sylow_b200_verify_batch_finish(sylow_b200_ctx* ctx, const uint8_t* partials /* n_partials*384 */,
-                                   size_t n_partials, int* ok);
-
-/* Single-GPU convenience: partial + finish. */
-int sylow_b200_verify_batch(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs, const uint64_t* offsets,
-                            const uint8_t* sigs, size_t n, const uint8_t* dst, size_t dst_len, int hash_id, int* ok);
+ * additions and two Miller loops for the whole batch.  Same verdict as the product form; weight_seed as above. */
+int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk /* 128 */, int pk_inf, const uint8_t* msgs,
+                                        const uint64_t* offsets, const uint8_t* sigs /* n*64 */, const uint8_t* sigs_inf,
+                                        size_t n, const uint8_t* dst, size_t dst_len, int hash_id,
+                                        const uint8_t* weight_seed /* 32 B or NULL */, int* ok);
 
 /* ---- device-resident variants (DEVICE pointers, asynchronous on `stream`) ----------------------- */
 
@@ -271,18 +303,28 @@ int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_pts, const
 int sylow_b200_hash_to_g1_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
                                     const uint8_t* dst, size_t dst_len /* host */, int hash_id, uint8_t* d_out,
                                     uint8_t* d_out_inf, void* stream);
-int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
-                                        const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n,
-                                        const uint8_t* dst, size_t dst_len /* host */, int hash_id,
+int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_pks_inf,
+                                        const uint8_t* d_msgs, const uint64_t* d_offsets, const uint8_t* d_sigs,
+                                        const uint8_t* d_sigs_inf, size_t n, const uint8_t* dst,
+                                        size_t dst_len /* host */, int hash_id,
+                                        const uint8_t* weight_seed /* host, 32 B or NULL */, uint64_t first_index,
                                         uint8_t* d_f_out /* 384 */, void* stream);
+/* The hashing `_dev` calls (hash_to_g1_batch_dev, verify_batch_partial_dev) cannot return GroupError::CannotHashToGroup
+ * themselves: this synchronises `stream`, sets *failed = 1 if a hash-to-curve of the LAST such call failed (SvdW's
+ * square-root check, svdw.rs:253-261), and clears the flag.  Every hashing call clears the flag when it starts. */
+int sylow_b200_hash_failed_dev(sylow_b200_ctx* ctx, void* stream, int* failed);
 
 /* ---- diagnostics used by the parity tests and the roofline microbenchmark ---------------------- */
 
-/* out[i] = a[i] (op) b[i] on canonical Fp values; op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 a/2, 5 -a. */
+/* out[i] = a[i] (op) b[i] on canonical Fp values; op: 0 mul, 1 add, 2 sub, 3 inv(a) (binary GCD), 4 a/2, 5 -a,
+ * 6 inv(a) by the Fermat ladder, 7 raw output (a / p) + 1 from the Jacobi iteration, + 4 if a^((p-1)/2) disagrees. */
 int sylow_b200_fp_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 /* out[i] = a[i] (op) b[i] on Fp12; op: 0 mul, 1 sqr(a), 2 inv(a), 3/4/5 frobenius^{1,2,3}(a),
  * 6 cyclotomic_squared(a), 7 a.sparse_mul(b.c0.c0, b.c0.c1, b.c0.c2). */
 int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+/* out[i] = the batch-verification weight r_(first_index + i) derived from weight_seed (tests). */
+int sylow_b200_batch_weights(sylow_b200_ctx* ctx, const uint8_t* weight_seed /* 32 B */, uint64_t first_index, size_t n,
+                             uint64_t* out);
 /* Register-resident throughput probes (the IMAD roofline denominator).  Every thread
  * runs `iters` loop iterations.  variant 0/1/2: 1/2/4 interleaved dependent Montgomery multiplications
  * per iteration (*ops_out = Fp multiplications; x136 = limb products).  variant 10: independent

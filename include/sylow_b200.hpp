@@ -12,7 +12,6 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "sylow_b200.h"
@@ -50,6 +49,12 @@ struct Error : std::runtime_error {
 class Engine {
  public:
   explicit Engine(int device = 0) { ck(sylow_b200_create(&ctx_, device), "sylow_b200_create"); }
+  // One context over several GPUs (sylow_b200_create_multi): every batched call below shards its batch as
+  // contiguous slices inside the library; results are bit-identical to the single-device call.
+  explicit Engine(const std::vector<int>& devices) {
+    ck(sylow_b200_create_multi(&ctx_, devices.data(), (int)devices.size()), "sylow_b200_create_multi");
+  }
+  size_t device_count() const { return (size_t)sylow_b200_device_count(ctx_); }
   ~Engine() { if (ctx_) sylow_b200_destroy(ctx_); }
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
@@ -145,33 +150,39 @@ class Engine {
                                    const std::string& dst = DST()) {
     size_t n = same(sks.size(), msgs.size());
     Msgs m(msgs);
-    std::vector<std::uint8_t> out(n * 64);
+    std::vector<std::uint8_t> out(n * 64), inf(n + 1);
     ck(sylow_b200_sign_batch(ctx_, reinterpret_cast<const std::uint8_t*>(sks.data()), m.buf.data(), m.offs.data(), n,
-                             udata(dst), dst.size(), SYLOW_B200_HASH_KECCAK256, out.data()), "sign_batch");
+                             udata(dst), dst.size(), SYLOW_B200_HASH_KECCAK256, out.data(), inf.data()), "sign_batch");
     std::vector<G1Affine> r(n);
-    for (size_t i = 0; i < n; i++) std::memcpy(&r[i].x, &out[64 * i], 64);
+    for (size_t i = 0; i < n; i++) { std::memcpy(&r[i].x, &out[64 * i], 64); r[i].infinity = inf[i]; }
     return r;
   }
-  // verify(&G2Projective, &[u8], &G1Projective) per signature (lib.rs:223-236)
+  // verify(&G2Projective, &[u8], &G1Projective) per signature (lib.rs:223-236); identity keys / signatures follow
+  // pairing()'s infinity rule (pairing.rs:876-886) inside the library
   std::vector<bool> verify_each(const std::vector<G2Affine>& pks, const std::vector<std::string>& msgs,
                                 const std::vector<G1Affine>& sigs, const std::string& dst = DST()) {
     size_t n = same(pks.size(), same(msgs.size(), sigs.size()));
     Msgs m(msgs);
     Packed pk = pack(pks), sg = pack(sigs);
     std::vector<std::uint8_t> ok(n);
-    ck(sylow_b200_verify_each(ctx_, pk.pts.data(), m.buf.data(), m.offs.data(), sg.pts.data(), n, udata(dst), dst.size(),
-                              SYLOW_B200_HASH_KECCAK256, ok.data()), "verify_each");
+    ck(sylow_b200_verify_each(ctx_, pk.pts.data(), pk.inf.data(), m.buf.data(), m.offs.data(), sg.pts.data(),
+                              sg.inf.data(), n, udata(dst), dst.size(), SYLOW_B200_HASH_KECCAK256, ok.data()),
+       "verify_each");
     return std::vector<bool>(ok.begin(), ok.end());
   }
-  // batch form with one final exponentiation (examples/verify_multiple_messages_same_signer.rs:40-60)
+  // The product check with one final exponentiation (examples/verify_multiple_messages_same_signer.rs:40-60).
+  // weight_seed == nullptr: the reference example's unweighted product (aggregate verification);
+  // 32 secret random bytes: batch verification with random 64-bit weights (sound per signature).
   bool verify_batch(const std::vector<G2Affine>& pks, const std::vector<std::string>& msgs,
-                    const std::vector<G1Affine>& sigs, const std::string& dst = DST()) {
+                    const std::vector<G1Affine>& sigs, const std::string& dst = DST(),
+                    const std::array<std::uint8_t, 32>* weight_seed = nullptr) {
     size_t n = same(pks.size(), same(msgs.size(), sigs.size()));
     Msgs m(msgs);
     Packed pk = pack(pks), sg = pack(sigs);
     int ok = 0;
-    ck(sylow_b200_verify_batch(ctx_, pk.pts.data(), m.buf.data(), m.offs.data(), sg.pts.data(), n, udata(dst), dst.size(),
-                               SYLOW_B200_HASH_KECCAK256, &ok), "verify_batch");
+    ck(sylow_b200_verify_batch(ctx_, pk.pts.data(), pk.inf.data(), m.buf.data(), m.offs.data(), sg.pts.data(),
+                               sg.inf.data(), n, udata(dst), dst.size(), SYLOW_B200_HASH_KECCAK256,
+                               weight_seed ? weight_seed->data() : nullptr, &ok), "verify_batch");
     return ok != 0;
   }
   bool verify(const G2Affine& pk, const std::string& msg, const G1Affine& sig) { return verify_each({pk}, {msg}, {sig})[0]; }
@@ -205,91 +216,12 @@ class Engine {
   sylow_b200_ctx* ctx_ = nullptr;
 };
 
-// One Engine per GPU: a batch is cut into contiguous slices, one host thread drives each context, and
-// the per-item results are concatenated.  The only exchange the path has is in the product form: `verify_batch` takes
-// the 384-byte Miller partial of every GPU and finishes with 7 Fp12 products and ONE final exponentiation.
-class MultiEngine {
+// One context over several GPUs.  The slicing, the per-GPU host threads and the combination of the
+// 384-byte Miller partials live inside the library (sylow_b200_create_multi), so this is the same class.
+class MultiEngine : public Engine {
  public:
-  explicit MultiEngine(const std::vector<int>& devices) {
-    if (devices.empty()) throw Error(SYLOW_B200_ERR_ARG, "MultiEngine: no devices");
-    for (int d : devices) eng_.emplace_back(new Engine(d));
-  }
-  size_t size() const { return eng_.size(); }
-  Engine& operator[](size_t i) { return *eng_[i]; }
-
-  std::vector<Gt> pairing_batch(const std::vector<G1Affine>& p, const std::vector<G2Affine>& q) {
-    if (p.size() != q.size()) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ");
-    std::vector<std::vector<Gt>> part(eng_.size());
-    run([&](size_t g, size_t lo, size_t hi) {
-      part[g] = eng_[g]->pairing_batch(slice(p, lo, hi), slice(q, lo, hi));
-    }, p.size());
-    std::vector<Gt> out;
-    out.reserve(p.size());
-    for (auto& v : part) out.insert(out.end(), v.begin(), v.end());
-    return out;
-  }
-  std::vector<G1Affine> g1_mul_batch(const std::vector<G1Affine>& pts, const std::vector<Fp>& k) {
-    if (pts.size() != k.size()) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ");
-    std::vector<std::vector<G1Affine>> part(eng_.size());
-    run([&](size_t g, size_t lo, size_t hi) { part[g] = eng_[g]->g1_mul_batch(slice(pts, lo, hi), slice(k, lo, hi)); },
-        pts.size());
-    std::vector<G1Affine> out;
-    for (auto& v : part) out.insert(out.end(), v.begin(), v.end());
-    return out;
-  }
-  // prod_i e(sig_i, G2gen) e(-H(m_i), pk_i) == 1 over all GPUs
-  bool verify_batch(const std::vector<G2Affine>& pks, const std::vector<std::string>& msgs,
-                    const std::vector<G1Affine>& sigs, const std::string& dst = DST()) {
-    if (pks.size() != msgs.size() || msgs.size() != sigs.size()) throw Error(SYLOW_B200_ERR_ARG, "batch sizes differ");
-    std::vector<std::uint8_t> partials(eng_.size() * 384);
-    run([&](size_t g, size_t lo, size_t hi) {
-      std::vector<std::uint8_t> pk((hi - lo) * 128 + 16), sg((hi - lo) * 64 + 16), buf;
-      std::vector<std::uint64_t> offs{0};
-      for (size_t i = lo; i < hi; i++) {
-        std::memcpy(&pk[128 * (i - lo)], &pks[i].x, 128);
-        std::memcpy(&sg[64 * (i - lo)], &sigs[i].x, 64);
-        buf.insert(buf.end(), msgs[i].begin(), msgs[i].end());
-        offs.push_back(buf.size());
-      }
-      if (buf.empty()) buf.push_back(0);
-      int st = sylow_b200_verify_batch_partial(eng_[g]->raw(), pk.data(), buf.data(), offs.data(), sg.data(), hi - lo,
-                                               reinterpret_cast<const std::uint8_t*>(dst.data()), dst.size(),
-                                               SYLOW_B200_HASH_KECCAK256, &partials[384 * g]);
-      if (st != 0) throw Error(st, "verify_batch_partial");
-    }, msgs.size());
-    int ok = 0;
-    int st = sylow_b200_verify_batch_finish(eng_[0]->raw(), partials.data(), eng_.size(), &ok);
-    if (st != 0) throw Error(st, "verify_batch_finish");
-    return ok != 0;
-  }
-
- private:
-  template <class T>
-  static std::vector<T> slice(const std::vector<T>& v, size_t lo, size_t hi) {
-    return std::vector<T>(v.begin() + lo, v.begin() + hi);
-  }
-  // fn(g, lo, hi) on one thread per context over the contiguous slice [g n / G, (g + 1) n / G)
-  template <class F>
-  void run(F fn, size_t n) {
-    std::vector<std::thread> th;
-    std::vector<std::string> err(eng_.size());
-    std::vector<int> status(eng_.size(), 0);
-    for (size_t g = 0; g < eng_.size(); g++) {
-      size_t lo = g * n / eng_.size(), hi = (g + 1) * n / eng_.size();
-      th.emplace_back([&, g, lo, hi] {
-        try {
-          fn(g, lo, hi);
-        } catch (const Error& e) {
-          status[g] = e.status;
-          err[g] = e.what();
-        }
-      });
-    }
-    for (auto& t : th) t.join();
-    for (size_t g = 0; g < eng_.size(); g++)
-      if (status[g] != 0) throw Error(status[g], err[g].c_str());
-  }
-  std::vector<std::unique_ptr<Engine>> eng_;
+  explicit MultiEngine(const std::vector<int>& devices) : Engine(devices) {}
+  size_t size() const { return device_count(); }
 };
 
 }  // namespace sylow

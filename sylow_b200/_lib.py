@@ -20,6 +20,9 @@ HASH_SHAKE128 = 2
 _P = c_void_p
 _SIGNATURES = {
     "sylow_b200_create": (c_int, [POINTER(c_void_p), c_int]),
+    "sylow_b200_create_multi": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int]),
+    "sylow_b200_device_count": (c_int, [_P]),
+    "sylow_b200_device_ctx": (c_void_p, [_P, c_int]),
     "sylow_b200_destroy": (c_int, [_P]),
     "sylow_b200_strerror": (c_char_p, [c_int]),
     "sylow_b200_last_cuda_error": (c_int, [_P]),
@@ -51,14 +54,18 @@ _SIGNATURES = {
     "sylow_b200_g1_msm_bucket": (c_int, [_P, _P, _P, _P, c_size_t, c_int, _P, _P]),
     "sylow_b200_lagrange_coefficients_batch": (c_int, [_P, _P, c_size_t, c_size_t, _P]),
     "sylow_b200_threshold_aggregate_batch": (c_int, [_P, _P, _P, _P, c_size_t, c_size_t, _P, _P]),
-    "sylow_b200_verify_batch_same_signer": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, POINTER(c_int)]),
+    "sylow_b200_verify_batch_same_signer": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P,
+                                                    POINTER(c_int)]),
     "sylow_b200_expand_message_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, c_size_t, _P]),
     "sylow_b200_hash_to_field_batch": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
-    "sylow_b200_sign_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
-    "sylow_b200_verify_each": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
-    "sylow_b200_verify_batch_partial": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
+    "sylow_b200_sign_batch": (c_int, [_P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P]),
+    "sylow_b200_verify_each": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P]),
+    "sylow_b200_verify_batch_partial": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, c_uint64,
+                                                _P]),
     "sylow_b200_verify_batch_finish": (c_int, [_P, _P, c_size_t, POINTER(c_int)]),
-    "sylow_b200_verify_batch": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, POINTER(c_int)]),
+    "sylow_b200_verify_batch": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, POINTER(c_int)]),
+    "sylow_b200_hash_failed_dev": (c_int, [_P, _P, POINTER(c_int)]),
+    "sylow_b200_batch_weights": (c_int, [_P, _P, c_uint64, c_size_t, _P]),
     "sylow_b200_pairing_batch_dev": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_miller_loop_batch_dev": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "sylow_b200_miller_product_dev": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, _P]),
@@ -67,7 +74,8 @@ _SIGNATURES = {
     "sylow_b200_g1_mul_batch_dev": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P, _P]),
     "sylow_b200_g2_mul_batch_dev": (c_int, [_P, _P, _P, _P, c_size_t, _P, _P, _P]),
     "sylow_b200_hash_to_g1_batch_dev": (c_int, [_P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P, _P]),
-    "sylow_b200_verify_batch_partial_dev": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P, _P]),
+    "sylow_b200_verify_batch_partial_dev": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int, _P,
+                                                    c_uint64, _P, _P]),
     "sylow_b200_fp_op_batch": (c_int, [_P, c_int, _P, _P, c_size_t, _P]),
     "sylow_b200_fp12_op_batch": (c_int, [_P, c_int, _P, _P, c_size_t, _P]),
     "sylow_b200_imad_probe": (c_int, [_P, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_double)]),

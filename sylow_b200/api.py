@@ -41,16 +41,26 @@ def pack_messages(msgs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
 
 
 class Engine:
-    """One context bound to one CUDA device (one process per GPU)."""
+    """One context: bound to one CUDA device (`Engine(0)`, one process per GPU) or, given a list of devices
+    (`Engine([0, 1, 2, 3])`, sylow_b200_create_multi), sharding every batched host-buffer call over them."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._lib = _lib.load()
         h = ctypes.c_void_p()
-        st = self._lib.sylow_b200_create(ctypes.byref(h), int(device))
+        if isinstance(device, (list, tuple)):
+            ids = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            st = self._lib.sylow_b200_create_multi(ctypes.byref(h), ids, len(device))
+            self.device = int(device[0]) if device else 0
+        else:
+            st = self._lib.sylow_b200_create(ctypes.byref(h), int(device))
+            self.device = int(device)
         if st != 0:
-            raise _lib.SylowB200Error(st, "sylow_b200_create(device=%d)" % device)
+            raise _lib.SylowB200Error(st, "sylow_b200_create(device=%r)" % (device,))
         self._h = h
-        self.device = int(device)
+
+    @property
+    def device_count(self) -> int:
+        return int(self._lib.sylow_b200_device_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -332,16 +342,39 @@ class Engine:
         return out, inf
 
     # ------------------------------------------------------------------ hash / BLS
-    def verify_batch_same_signer(self, pk, msgs, sigs, dst: bytes = DST) -> bool:
+    @staticmethod
+    def _flags(f, n):
+        return None if f is None else np.ascontiguousarray(f, dtype=np.uint8).reshape(n)
+
+    @staticmethod
+    def _seed(weight_seed):
+        """32 secret random bytes (batch verification) or None (the reference example's unweighted product)."""
+        if weight_seed is None:
+            return None
+        seed = np.frombuffer(bytes(weight_seed), dtype=np.uint8).copy()
+        if seed.size != 32:
+            raise ValueError("weight_seed must be 32 bytes")
+        return seed
+
+    def verify_batch_same_signer(self, pk, msgs, sigs, dst: bytes = DST, pk_inf: bool = False, sigs_inf=None,
+                                 weight_seed=None) -> bool:
         pk = np.ascontiguousarray(pk, dtype=np.uint8).reshape(128)
         sigs = _u8(sigs, 64, "sigs")
         buf, offs = self._msgs(msgs)
         n = offs.size - 1
         ok = ctypes.c_int(0)
-        self._ck(self._lib.sylow_b200_verify_batch_same_signer(self._h, _ptr(pk), _ptr(buf), _ptr(offs), _ptr(sigs), n,
-                                                               dst, len(dst), _lib.HASH_KECCAK256, ctypes.byref(ok)),
+        seed = self._seed(weight_seed)
+        self._ck(self._lib.sylow_b200_verify_batch_same_signer(self._h, _ptr(pk), int(bool(pk_inf)), _ptr(buf), _ptr(offs),
+                                                               _ptr(sigs), _ptr(self._flags(sigs_inf, n)), n, dst, len(dst),
+                                                               _lib.HASH_KECCAK256, _ptr(seed), ctypes.byref(ok)),
                  "verify_batch_same_signer")
         return bool(ok.value)
+
+    def batch_weights(self, weight_seed, first_index: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint64)
+        self._ck(self._lib.sylow_b200_batch_weights(self._h, _ptr(self._seed(weight_seed)), int(first_index), n, _ptr(out)),
+                 "batch_weights")
+        return out
 
     @staticmethod
     def _msgs(msgs):
@@ -378,33 +411,39 @@ class Engine:
                                                           _ptr(out)), "hash_to_field_batch")
         return out
 
-    def sign_batch(self, sks, msgs, dst: bytes = DST) -> np.ndarray:
+    def sign_batch(self, sks, msgs, dst: bytes = DST, return_inf: bool = False):
         sks = _u8(sks, 32, "sks")
         buf, offs = self._msgs(msgs)
         n = offs.size - 1
         out = np.empty((n, 64), dtype=np.uint8)
+        inf = np.zeros(n, dtype=np.uint8)
         self._ck(self._lib.sylow_b200_sign_batch(self._h, _ptr(sks), _ptr(buf), _ptr(offs), n, dst, len(dst),
-                                                 _lib.HASH_KECCAK256, _ptr(out)), "sign_batch")
-        return out
+                                                 _lib.HASH_KECCAK256, _ptr(out), _ptr(inf)), "sign_batch")
+        return (out, inf) if return_inf else out
 
-    def verify_each(self, pks, msgs, sigs, dst: bytes = DST) -> np.ndarray:
+    def verify_each(self, pks, msgs, sigs, dst: bytes = DST, pks_inf=None, sigs_inf=None) -> np.ndarray:
         pks = _u8(pks, 128, "pks")
         sigs = _u8(sigs, 64, "sigs")
         buf, offs = self._msgs(msgs)
         n = offs.size - 1
         ok = np.empty(n, dtype=np.uint8)
-        self._ck(self._lib.sylow_b200_verify_each(self._h, _ptr(pks), _ptr(buf), _ptr(offs), _ptr(sigs), n, dst,
-                                                  len(dst), _lib.HASH_KECCAK256, _ptr(ok)), "verify_each")
+        self._ck(self._lib.sylow_b200_verify_each(self._h, _ptr(pks), _ptr(self._flags(pks_inf, n)), _ptr(buf), _ptr(offs),
+                                                  _ptr(sigs), _ptr(self._flags(sigs_inf, n)), n, dst, len(dst),
+                                                  _lib.HASH_KECCAK256, _ptr(ok)), "verify_each")
         return ok.astype(bool)
 
-    def verify_batch_partial(self, pks, msgs, sigs, dst: bytes = DST) -> np.ndarray:
+    def verify_batch_partial(self, pks, msgs, sigs, dst: bytes = DST, pks_inf=None, sigs_inf=None, weight_seed=None,
+                             first_index: int = 0) -> np.ndarray:
         pks = _u8(pks, 128, "pks")
         sigs = _u8(sigs, 64, "sigs")
         buf, offs = self._msgs(msgs)
         n = offs.size - 1
         out = np.empty(384, dtype=np.uint8)
-        self._ck(self._lib.sylow_b200_verify_batch_partial(self._h, _ptr(pks), _ptr(buf), _ptr(offs), _ptr(sigs), n,
-                                                           dst, len(dst), _lib.HASH_KECCAK256, _ptr(out)),
+        seed = self._seed(weight_seed)
+        self._ck(self._lib.sylow_b200_verify_batch_partial(self._h, _ptr(pks), _ptr(self._flags(pks_inf, n)), _ptr(buf),
+                                                           _ptr(offs), _ptr(sigs), _ptr(self._flags(sigs_inf, n)), n,
+                                                           dst, len(dst), _lib.HASH_KECCAK256, _ptr(seed),
+                                                           int(first_index), _ptr(out)),
                  "verify_batch_partial")
         return out
 
@@ -415,8 +454,19 @@ class Engine:
                                                           ctypes.byref(ok)), "verify_batch_finish")
         return bool(ok.value)
 
-    def verify_batch(self, pks, msgs, sigs, dst: bytes = DST) -> bool:
-        return self.verify_batch_finish(self.verify_batch_partial(pks, msgs, sigs, dst).reshape(1, 384))
+    def verify_batch(self, pks, msgs, sigs, dst: bytes = DST, pks_inf=None, sigs_inf=None, weight_seed=None) -> bool:
+        """weight_seed=None: the reference example's aggregate check (prod e(sig_i, G2) e(-H_i, pk_i) == 1);
+        32 random bytes: batch verification with random 64-bit weights (sound per signature)."""
+        pks = _u8(pks, 128, "pks")
+        sigs = _u8(sigs, 64, "sigs")
+        buf, offs = self._msgs(msgs)
+        n = offs.size - 1
+        ok = ctypes.c_int(0)
+        seed = self._seed(weight_seed)
+        self._ck(self._lib.sylow_b200_verify_batch(self._h, _ptr(pks), _ptr(self._flags(pks_inf, n)), _ptr(buf), _ptr(offs),
+                                                   _ptr(sigs), _ptr(self._flags(sigs_inf, n)), n, dst, len(dst),
+                                                   _lib.HASH_KECCAK256, _ptr(seed), ctypes.byref(ok)), "verify_batch")
+        return bool(ok.value)
 
     # ------------------------------------------------------------------ diagnostics
     def fp_op_batch(self, op: int, a, b) -> np.ndarray:
@@ -502,9 +552,19 @@ class Engine:
                                                            self._tp(d_out_inf), self._stream()),
                  "hash_to_g1_batch_dev")
 
-    def verify_batch_partial_dev(self, d_pks, d_msgs, d_offsets, d_sigs, d_f_out, dst: bytes = DST):
+    def verify_batch_partial_dev(self, d_pks, d_msgs, d_offsets, d_sigs, d_f_out, dst: bytes = DST, d_pks_inf=None,
+                                 d_sigs_inf=None, weight_seed=None, first_index: int = 0):
         n = d_offsets.shape[0] - 1
-        self._ck(self._lib.sylow_b200_verify_batch_partial_dev(self._h, self._tp(d_pks), self._tp(d_msgs),
-                                                               self._tp(d_offsets), self._tp(d_sigs), n, dst,
-                                                               len(dst), _lib.HASH_KECCAK256, self._tp(d_f_out),
-                                                               self._stream()), "verify_batch_partial_dev")
+        seed = self._seed(weight_seed)
+        self._ck(self._lib.sylow_b200_verify_batch_partial_dev(self._h, self._tp(d_pks), self._tp(d_pks_inf),
+                                                               self._tp(d_msgs), self._tp(d_offsets), self._tp(d_sigs),
+                                                               self._tp(d_sigs_inf), n, dst, len(dst),
+                                                               _lib.HASH_KECCAK256, _ptr(seed), int(first_index),
+                                                               self._tp(d_f_out), self._stream()),
+                 "verify_batch_partial_dev")
+
+    def hash_failed_dev(self) -> bool:
+        """True if a hash-to-curve of the last hashing `_dev` call failed (synchronises the stream, clears the flag)."""
+        f = ctypes.c_int(0)
+        self._ck(self._lib.sylow_b200_hash_failed_dev(self._h, self._stream(), ctypes.byref(f)), "hash_failed_dev")
+        return bool(f.value)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libsylow_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    "-shared", "-Xcompiler", "-fPIC,-pthread", "-Xptxas", "-v",
 ]
 
 

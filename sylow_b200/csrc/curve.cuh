@@ -161,6 +161,25 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul(const Proj<F>& p, const uint32_t* k) {
   return acc;
 }
 
+// k * P for a 64-bit k (the random weights of batch verification): 16 windows of 4 bits.
+template <class F>
+SY_HD_NOINLINE Proj<F> proj_scalar_mul_u64(const Proj<F>& p, uint64_t k) {
+  Proj<F> tab[16];
+  tab[0] = proj_zero<F>();
+  tab[1] = p;
+  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
+  Proj<F> acc = tab[(uint32_t)(k >> 60)];
+  for (int w = 14; w >= 0; w--) {
+    SY_LOOP_SYNC();
+    acc = proj_double(acc);
+    acc = proj_double(acc);
+    acc = proj_double(acc);
+    acc = proj_double(acc);
+    acc = proj_add(acc, tab[(uint32_t)(k >> (4 * w)) & 15u]);
+  }
+  return acc;
+}
+
 // ---- GLV scalar multiplication --------------------------------------------------------------------
 // phi(x, y) = (beta x, y) is an endomorphism of both curves (j = 0) and acts on the r-torsion as
 // multiplication by lambda, lambda^2 + lambda + 1 = 0 mod r.  k = k1 + k2 lambda (mod r) with

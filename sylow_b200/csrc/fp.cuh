@@ -41,31 +41,8 @@
 #ifndef SY_BLOCK_SYNC
 #define SY_BLOCK_SYNC 1
 #endif
-// SY_STAGGER (cycles): after each re-convergence the warps that share a scheduler with a lower-numbered warp
-// (warp id / 4 = 1, 2, ...) wait g * SY_STAGGER cycles.  Warps in lockstep are in the same phase of the code
-// (all in a multiplication or all in a carry chain) and queue on ONE pipe; a small skew lets one warp's
-// IMAD phase overlap the other's ALU phase while both stay inside the same instruction-cache window.
-#ifndef SY_STAGGER
-#define SY_STAGGER 0
-#endif
-#if defined(__CUDA_ARCH__) && defined(SY_ROLE_SYNC)
-// experiment: two 128-thread roles per 256-thread block, each re-converging on its own named barrier
-#define SY_LOOP_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(1 + (threadIdx.x >> 7)))
-#elif defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
-#if SY_STAGGER > 0
-__device__ __forceinline__ void sy_stagger() {
-  unsigned g = threadIdx.x >> 7;  // warp id / 4: position of this warp on its scheduler
-  if (g) {
-    long long t0 = clock64();
-    long long d = (long long)g * SY_STAGGER;
-    while (clock64() - t0 < d) {
-    }
-  }
-}
-#define SY_LOOP_SYNC() (__syncthreads(), sy_stagger())
-#else
+#if defined(__CUDA_ARCH__) && SY_BLOCK_SYNC >= 1
 #define SY_LOOP_SYNC() __syncthreads()
-#endif
 #else
 #define SY_LOOP_SYNC() ((void)0)
 #endif
@@ -271,6 +248,38 @@ SY_HD Fp fp_halve(const Fp& a) {
 SY_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
 SY_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
 
+// Four 32x32->64 products with no addend, one IMAD.WIDE each: (X[2k], X[2k+1]) = a_k * b.  Written as mul.wide.u32
+// because ptxas does not fuse a mul.lo / mul.hi pair (it emits IMAD + IMAD.HI, two multiplier-pipe instructions).
+#ifndef SY_MULWIDE
+#define SY_MULWIDE 1
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void mul_row4(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if SY_MULWIDE
+  asm("{\n\t"
+      ".reg .u64 t0, t1, t2, t3;\n\t"
+      "mul.wide.u32 t0, %8, %12;\n\t"
+      "mul.wide.u32 t1, %9, %12;\n\t"
+      "mul.wide.u32 t2, %10, %12;\n\t"
+      "mul.wide.u32 t3, %11, %12;\n\t"
+      "mov.b64 {%0, %1}, t0;\n\t"
+      "mov.b64 {%2, %3}, t1;\n\t"
+      "mov.b64 {%4, %5}, t2;\n\t"
+      "mov.b64 {%6, %7}, t3;\n\t"
+      "}"
+      : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+  asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
+      : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#endif
+}
+#endif
+
 // ---- Montgomery multiplication ------------------------------------------------------------------
 // One CIOS round for multiplier limb bi.  T = X + Y * 2^32 (X: columns at limbs 0,2,4,6; Y: columns at
 // limbs 1,3,5,7).  After the round X[0] == 0 and the caller swaps the roles of X and Y, which divides
@@ -279,18 +288,8 @@ SY_HD Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
 template <bool FIRST>
 __device__ __forceinline__ void mont_round(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
   if (FIRST) {
-    asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
-        "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
-        "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
-        "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
-        : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
-        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
-    asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
-        "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
-        "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
-        "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
-        : "=r"(Y[0]), "=r"(Y[1]), "=r"(Y[2]), "=r"(Y[3]), "=r"(Y[4]), "=r"(Y[5]), "=r"(Y[6]), "=r"(Y[7])
-        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+    mul_row4(X, a[0], a[2], a[4], a[6], bi);
+    mul_row4(Y, a[1], a[3], a[5], a[7], bi);
   } else {
     // X[0] += Y[1]; Y = (Y >> 64) + a_odd * bi   (carry of the first add feeds the chain)
     asm("add.cc.u32 %0, %0, %2;\n\t"
@@ -439,12 +438,7 @@ __device__ __forceinline__ void wide_row_fresh(uint32_t* X, uint32_t a0, uint32_
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
 __device__ __forceinline__ void wide_row_first(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
-  asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
-      "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
-      "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
-      "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
-      : "=r"(X[0]), "=r"(X[1]), "=r"(X[2]), "=r"(X[3]), "=r"(X[4]), "=r"(X[5]), "=r"(X[6]), "=r"(X[7])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+  mul_row4(X, a0, a1, a2, a3, b);
 }
 
 // T = a * b.  E collects the products whose position i+j is even, O (offset by one limb) the others;
@@ -498,12 +492,7 @@ __device__ __forceinline__ void redc_round(uint32_t* X, uint32_t* Y) {
   uint32_t m;
   if (FIRST) {
     m = X[0] * SY_INV;
-    asm("mul.lo.u32 %0, %8, " SY_STR(SY_P1) "; mul.hi.u32 %1, %8, " SY_STR(SY_P1) ";\n\t"
-        "mul.lo.u32 %2, %8, " SY_STR(SY_P3) "; mul.hi.u32 %3, %8, " SY_STR(SY_P3) ";\n\t"
-        "mul.lo.u32 %4, %8, " SY_STR(SY_P5) "; mul.hi.u32 %5, %8, " SY_STR(SY_P5) ";\n\t"
-        "mul.lo.u32 %6, %8, " SY_STR(SY_P7) "; mul.hi.u32 %7, %8, " SY_STR(SY_P7) ";"
-        : "=r"(Y[0]), "=r"(Y[1]), "=r"(Y[2]), "=r"(Y[3]), "=r"(Y[4]), "=r"(Y[5]), "=r"(Y[6]), "=r"(Y[7])
-        : "r"(m));
+    mul_row4(Y, SY_P1, SY_P3, SY_P5, SY_P7, m);
   } else {
     // X[0] += Y[1]; m = X[0] * inv; Y = (Y >> 64) + m * p_odd   (the fold carry feeds the chain)
     asm("add.cc.u32 %0, %0, %2;\n\t"
@@ -724,130 +713,7 @@ inline void fp_add_nr(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 }
 #endif
 
-// ---- lazy reduction above Fp2 (tower.cuh fp6_mul): sums of unreduced 512-bit products ----------------
-// Values are kept mod 2^512 (additions and subtractions wrap); only the FINAL value of each accumulation has to lie
-// in [0, 2^512) = [0, 27.98 p^2), which the caller arranges with one offset k * p * 2^253 (0.661 p^2 per unit).
-SY_DEFINE_TABLE(uint32_t, kWideOff2, 9, 0xc0000000u, 0xb61f3f51u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu)
-SY_DEFINE_TABLE(uint32_t, kWideOff4, 9, 0x80000000u, 0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u)
-SY_DEFINE_TABLE(uint32_t, kWideOff5, 9, 0x60000000u, 0x474e1e4cu, 0x4594578eu, 0xe1471e98u, 0x7eb0e29au, 0x10f0d73au, 0x13322b92u, 0xccbf041au, 0x1e3eb107u)
-SY_DEFINE_TABLE(uint32_t, kWideOff20, 9, 0x80000000u, 0x1d387931u, 0x16515e39u, 0x851c7a61u, 0xfac38a6bu, 0x43c35ce9u, 0x4cc8ae48u, 0x32fc1068u, 0x78fac41fu)
-SY_DEFINE_TABLE(uint32_t, kP2, 8, 0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u)
-SY_DEFINE_TABLE(uint32_t, kP4, 8, 0x61f3f51cu, 0xf082305bu, 0xa1c72a34u, 0x5e05aa45u, 0x06056176u, 0xe14116dau, 0x84c680a6u, 0xc19139cbu)
-
-// a += b, 16 limbs, mod 2^512
-SY_HD void wide_add(uint32_t* a, const uint32_t* b) {
-#if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %0, %16;\n\t"
-      "addc.cc.u32 %1, %1, %17;\n\t"
-      "addc.cc.u32 %2, %2, %18;\n\t"
-      "addc.cc.u32 %3, %3, %19;\n\t"
-      "addc.cc.u32 %4, %4, %20;\n\t"
-      "addc.cc.u32 %5, %5, %21;\n\t"
-      "addc.cc.u32 %6, %6, %22;\n\t"
-      "addc.cc.u32 %7, %7, %23;\n\t"
-      "addc.cc.u32 %8, %8, %24;\n\t"
-      "addc.cc.u32 %9, %9, %25;\n\t"
-      "addc.cc.u32 %10, %10, %26;\n\t"
-      "addc.cc.u32 %11, %11, %27;\n\t"
-      "addc.cc.u32 %12, %12, %28;\n\t"
-      "addc.cc.u32 %13, %13, %29;\n\t"
-      "addc.cc.u32 %14, %14, %30;\n\t"
-      "addc.u32 %15, %15, %31;"
-      : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
-        "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
-      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
-        "r"(b[10]), "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
-#else
-  uint64_t c = 0;
-  for (int i = 0; i < 16; i++) {
-    c += (uint64_t)a[i] + b[i];
-    a[i] = (uint32_t)c;
-    c >>= 32;
-  }
-#endif
-}
-// a += off * 2^224 for a 9-limb constant (the k * p * 2^253 offsets above), mod 2^512
-SY_HD void wide_add_off(uint32_t* a, const uint32_t* off) {
-#if defined(__CUDA_ARCH__)
-  asm("add.cc.u32 %0, %0, %9;\n\t"
-      "addc.cc.u32 %1, %1, %10;\n\t"
-      "addc.cc.u32 %2, %2, %11;\n\t"
-      "addc.cc.u32 %3, %3, %12;\n\t"
-      "addc.cc.u32 %4, %4, %13;\n\t"
-      "addc.cc.u32 %5, %5, %14;\n\t"
-      "addc.cc.u32 %6, %6, %15;\n\t"
-      "addc.cc.u32 %7, %7, %16;\n\t"
-      "addc.u32 %8, %8, %17;"
-      : "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
-      : "r"(off[0]), "r"(off[1]), "r"(off[2]), "r"(off[3]), "r"(off[4]), "r"(off[5]), "r"(off[6]), "r"(off[7]),
-        "r"(off[8]));
-#else
-  uint64_t c = 0;
-  for (int i = 0; i < 9; i++) {
-    c += (uint64_t)a[7 + i] + off[i];
-    a[7 + i] = (uint32_t)c;
-    c >>= 32;
-  }
-#endif
-}
-// a = 9 a mod 2^512
-SY_HD void wide_mul9(uint32_t* a) {
-  uint32_t t[16];
-#pragma unroll
-  for (int i = 15; i > 0; i--) t[i] = (a[i] << 3) | (a[i - 1] >> 29);
-  t[0] = a[0] << 3;
-  wide_add(a, t);
-}
-// a -= k if a >= k (8 limbs)
-SY_HD void fp_cond_sub(uint32_t* a, const uint32_t* k) {
-  uint32_t t[8], borrow;
-#if defined(__CUDA_ARCH__)
-  asm("sub.cc.u32 %0, %9, %17;\n\t"
-      "subc.cc.u32 %1, %10, %18;\n\t"
-      "subc.cc.u32 %2, %11, %19;\n\t"
-      "subc.cc.u32 %3, %12, %20;\n\t"
-      "subc.cc.u32 %4, %13, %21;\n\t"
-      "subc.cc.u32 %5, %14, %22;\n\t"
-      "subc.cc.u32 %6, %15, %23;\n\t"
-      "subc.cc.u32 %7, %16, %24;\n\t"
-      "subc.u32 %8, 0, 0;"
-      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(k[0]), "r"(k[1]),
-        "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]));
-#else
-  int64_t bw = 0;
-  for (int i = 0; i < 8; i++) {
-    int64_t d = (int64_t)a[i] - (int64_t)k[i] + bw;
-    t[i] = (uint32_t)d;
-    bw = d >> 32;
-  }
-  borrow = (uint32_t)bw;
-#endif
-#pragma unroll
-  for (int i = 0; i < 8; i++) a[i] = borrow ? a[i] : t[i];
-}
-// T * R^-1 mod p, fully reduced, for a "fat" T: the high half is first brought below p with STEPS conditional
-// subtractions (4p, 2p, p for 3; 2p, p for 2; p for 1), which needs T < 2^STEPS * p * 2^256.
-template <int STEPS>
-SY_HD Fp fp_redc_fat(const uint32_t* T) {
-  uint32_t U[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) U[i] = T[i];
-  if (STEPS >= 3) fp_cond_sub(U + 8, SY_TAB(kP4));
-  if (STEPS >= 2) fp_cond_sub(U + 8, SY_TAB(kP2));
-  if (STEPS >= 1) fp_cond_sub(U + 8, SY_TAB(kP));
-#if defined(SYLOW_HOSTSIM) && !defined(__CUDA_ARCH__)
-  {  // the bound analysis of the caller, checked on every value the host simulation sees: high half < p
-    int64_t bw = 0;
-    for (int i = 0; i < 8; i++) bw = ((int64_t)U[8 + i] - (int64_t)SY_TAB(kP)[i] + bw) >> 32;
-    if (bw == 0) {
-      fprintf(stderr, "fp_redc_fat<%d>: high half >= p\n", STEPS);
-      abort();
-    }
-  }
-#endif
-  return fp_redc_wide(U);
-}
+SY_DEFINE_TABLE(uint32_t, kP2, 8, 0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u)  // 2p
 
 // ---- 9 x + y + t mod p in one pass (the multiplications by xi = 9 + u, tower.cuh) --------------------------------
 // x, y, t < p, so T = 9x + y + t < 11p needs 9 limbs.  The quotient is estimated from the top 32 bits,
@@ -996,11 +862,7 @@ SY_HD Fp fp_mul3(const Fp& a) { return fp_add(fp_dbl(a), a); }
 // a^e for a fixed 256-bit exponent given as 8 LE words (uniform across the warp); top_bit = index of its
 // highest set bit.  Fixed 4-bit windows: 14 multiplications for the table, then 4 squarings and at most one
 // multiplication per window (the digit is uniform, so skipping a zero digit does not diverge).
-#ifndef SY_POW_WINDOW
-#define SY_POW_WINDOW 1
-#endif
 SY_HD_NOINLINE Fp fp_pow(const Fp& a, const uint32_t* e, int top_bit) {
-#if SY_POW_WINDOW
   Fp tab[16];
   tab[1] = a;
   tab[2] = fp_sqr(a);
@@ -1014,15 +876,6 @@ SY_HD_NOINLINE Fp fp_pow(const Fp& a, const uint32_t* e, int top_bit) {
     if (d) r = fp_mul(r, tab[d]);
   }
   return r;
-#else
-  Fp r = a;
-  for (int i = top_bit - 1; i >= 0; i--) {
-    if ((i & 15) == 15) SY_LOOP_SYNC();
-    r = fp_sqr(r);
-    if ((e[i >> 5] >> (i & 31)) & 1) r = fp_mul(r, a);
-  }
-  return r;
-#endif
 }
 
 // p-2, (p-1)/2, (p+1)/4 as LE words
@@ -1030,7 +883,162 @@ SY_DEFINE_TABLE(uint32_t, kPm2, 8, 0xd87cfd45, 0x3c208c16, 0x6871ca8d, 0x97816a9
 SY_DEFINE_TABLE(uint32_t, kPm1h, 8, 0x6c3e7ea3, 0x9e10460b, 0xb438e546, 0xcbc0b548, 0x40c0ac2e, 0xdc2822db, 0x7098d014, 0x18322739)
 SY_DEFINE_TABLE(uint32_t, kPp1q, 8, 0xb61f3f52, 0x4f082305, 0x5a1c72a3, 0x65e05aa4, 0xa0605617, 0x6e14116d, 0xb84c680a, 0x0c19139c)
 
-// inv(0) = 0 like the reference (fp.rs:418-424)
-SY_HD Fp fp_inv(const Fp& a) { return fp_pow(a, SY_TAB(kPm2), 253); }
+// ---- inversion and the quadratic character by a branch-free binary GCD ----------------------------------------------
+// Replaces the Fermat ladders x^(p-2) and x^((p-1)/2) (253 squarings + 75 products each, about 45 k IMAD.WIDE) by
+// 510 add/shift steps on 256-bit integers (about 60 ALU instructions each, no multiplier work).  Every lane runs the
+// same 510 steps; the data only feeds masks and selects.
+// One step on (a, n), n odd:   a even: a <- a / 2;   a odd: (a, n) <- (|a - n| / 2, min(a, n)).
+// bits(a) + bits(n) falls by at least one per step while a != 0, so 2 * 254 + 2 steps reach a = 0, n = gcd.
+// r = a - b mod 2^256; returns 0xffffffff when the subtraction borrowed (a < b), else 0
+SY_HD uint32_t u256_sub_b(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t borrow;
+#if defined(__CUDA_ARCH__)
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(borrow)
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+        "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+  int64_t bw = 0;
+  for (int i = 0; i < 8; i++) {
+    int64_t d = (int64_t)a[i] - (int64_t)b[i] + bw;
+    r[i] = (uint32_t)d;
+    bw = d >> 32;
+  }
+  borrow = (uint32_t)bw;
+#endif
+  return borrow;
+}
+// odd / sw are returned as masks: odd = a was odd, sw = a was odd and smaller than n (the pair was swapped)
+SY_HD void bingcd_step(uint32_t* a, uint32_t* n, uint32_t& odd, uint32_t& sw) {
+  uint32_t d[8], e[8];
+  odd = 0u - (a[0] & 1u);
+  uint32_t lt = u256_sub_b(d, a, n);  // d = a - n
+  fp_sub_nr(e, n, a);                 // e = n - a
+  sw = odd & lt;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint32_t y = lt ? e[i] : d[i];
+    d[i] = odd ? y : a[i];
+    n[i] = sw ? a[i] : n[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 7; i++) a[i] = (d[i] >> 1) | (d[i + 1] << 31);
+  a[7] = d[7] >> 1;
+}
+#define SY_GCD_STEPS 510  // 17 rounds of 30
+
+// Jacobi symbol (v / p) in {1, 0, -1} for v < p.  Montgomery form may be passed as is: R = 2^256 is a square.
+// Reciprocity when an odd pair is swapped (flip iff both are 3 mod 4) and (2 / n) for every halving (flip iff n is
+// 3 or 5 mod 8).  Once a = 0 the halving rule keeps running on n = gcd, which is 1 (no flip) - or p = 7 mod 8 for v = 0.
+SY_HD_NOINLINE int fp_jacobi(const Fp& v) {
+  uint32_t a[8], n[8], t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = v.l[i];
+    n[i] = SY_TAB(kP)[i];
+  }
+#pragma unroll 1
+  for (int it = 0; it < SY_GCD_STEPS; it++) {
+    uint32_t a0 = a[0], n0 = n[0], odd, sw;
+    bingcd_step(a, n, odd, sw);
+    t ^= ((a0 & n0) >> 1) & sw;
+    t ^= (n[0] >> 1) ^ (n[0] >> 2);
+  }
+  uint32_t rest = n[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < 8; i++) rest |= n[i];
+  return rest ? 0 : ((t & 1u) ? -1 : 1);
+}
+
+// (f u + g v) / 2^32 mod p for u, v < p and signed f, g with |f| + |g| <= 2^30: negative factors act on p - u, the sum
+// (< 2^30 p) takes one Montgomery step (< 1.25 p) and one conditional subtraction.
+SY_HD void bingcd_lincomb(uint32_t* r, int32_t f, const uint32_t* u, int32_t g, const uint32_t* v) {
+  uint32_t uu[8], vv[8], pp[8], T[9];
+#pragma unroll
+  for (int i = 0; i < 8; i++) pp[i] = SY_TAB(kP)[i];
+  fp_sub_nr(uu, pp, u);
+  fp_sub_nr(vv, pp, v);
+  bool fn = f < 0, gn = g < 0;
+  uint32_t fa = (uint32_t)(fn ? -f : f), ga = (uint32_t)(gn ? -g : g);
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    c += (uint64_t)fa * (fn ? uu[i] : u[i]);
+    uint64_t c2 = (uint64_t)ga * (gn ? vv[i] : v[i]);
+    uint64_t s = (c & 0xffffffffu) + (c2 & 0xffffffffu);
+    T[i] = (uint32_t)s;
+    c = (c >> 32) + (c2 >> 32) + (s >> 32);
+  }
+  T[8] = (uint32_t)c;
+  uint32_t m = T[0] * SY_INV;
+  c = ((uint64_t)m * pp[0] + T[0]) >> 32;
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    c += (uint64_t)m * pp[i] + T[i];
+    r[i - 1] = (uint32_t)c;
+    c >>= 32;
+  }
+  r[7] = (uint32_t)(c + T[8]);
+  fp_final_sub(r);
+}
+
+// 2^34 R^3 mod p: the 17 rounds leave v = y^-1 / 2^(17 (32 - 30)); the input is the Montgomery representative Y R, the
+// output must be Y^-1 R = (Y R)^-1 R^2, so the last step is one Montgomery product of v with 2^34 R^3.
+SY_HD Fp fp_gcd_fix() {
+  return Fp{{0x13bd45e1u, 0x31d6a0d9u, 0x382c59a2u, 0x45fbf2bcu, 0x1ab31dfbu, 0x5b5fa369u, 0xb36fd339u, 0x24811383u}};
+}
+// Invariant: a = u y c, n = v y c (mod p) with y the input integer.  30 steps are tracked as a 2 x 2 integer matrix
+// (entries below 2^30 in absolute value: row0 <- row0 - row1 when a is odd, row1 doubles every step, rows swap with
+// the pair), then applied to (u, v) at once.  inv(0) = 0 like the reference (fp.rs:418-424): a starts at 0 and v stays 0.
+SY_HD_NOINLINE Fp fp_inv(const Fp& y) {
+  uint32_t a[8], n[8], u[8], v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = y.l[i];
+    n[i] = SY_TAB(kP)[i];
+    u[i] = i == 0;
+    v[i] = 0;
+  }
+#pragma unroll 1
+  for (int round = 0; round < SY_GCD_STEPS / 30; round++) {
+    int32_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+#pragma unroll 1
+    for (int j = 0; j < 30; j++) {
+      uint32_t odd, sw;
+      bingcd_step(a, n, odd, sw);
+      int32_t tf = (f0 ^ f1) & (int32_t)sw, tg = (g0 ^ g1) & (int32_t)sw;
+      f0 ^= tf;
+      f1 ^= tf;
+      g0 ^= tg;
+      g1 ^= tg;
+      f0 -= f1 & (int32_t)odd;
+      g0 -= g1 & (int32_t)odd;
+      f1 <<= 1;
+      g1 <<= 1;
+    }
+    uint32_t nu[8], nv[8];
+    bingcd_lincomb(nu, f0, u, g0, v);
+    bingcd_lincomb(nv, f1, u, g1, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u[i] = nu[i];
+      v[i] = nv[i];
+    }
+  }
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = v[i];
+  return fp_mul(r, fp_gcd_fix());
+}
+// the Fermat ladder, kept as the cross-check of the tests (fp_op 7)
+SY_HD Fp fp_inv_fermat(const Fp& a) { return fp_pow(a, SY_TAB(kPm2), 253); }
 
 }  // namespace sylow

@@ -278,7 +278,9 @@ SY_HD void hash_to_field_keccak(const uint8_t* msg, size_t msg_len, const uint8_
   hash_to_field_xmd(0, msg, msg_len, dst_prime, dst_prime_len, u0, u1);
 }
 
-SY_HD bool fp_is_square(const Fp& a) {  // fp.rs:625-631 (true for 0)
+// fp.rs:625-631 (true for 0): the Legendre symbol through the binary-GCD Jacobi iteration (fp.cuh)
+SY_HD bool fp_is_square(const Fp& a) { return fp_jacobi(a) >= 0; }
+SY_HD bool fp_is_square_fermat(const Fp& a) {  // the reference's own x^((p-1)/2), cross-check for the tests
   Fp l = fp_pow(a, SY_TAB(kPm1h), 252);
   return fp_is_zero(l) | fp_eq(l, fp_one());
 }

@@ -1,0 +1,55 @@
+// The two kernels of the pairing step (BASELINE configs[1]): k_miller and k_final_exp, with their launch shapes.
+// Kept in a header so that the library (sylow_b200.cu) and the stand-alone timing harness (tools/kbench.cu) compile
+// exactly the same code.
+#pragma once
+#include "wire.cuh"
+
+#ifndef SY_MILLER_THREADS
+#define SY_MILLER_THREADS 128
+#endif
+#ifndef SY_MILLER_MINB
+#define SY_MILLER_MINB 2
+#endif
+#ifndef SY_FEXP_THREADS
+#define SY_FEXP_THREADS 384
+#endif
+#ifndef SY_FEXP_MINB
+#define SY_FEXP_MINB 1
+#endif
+
+namespace sylow_kernels {
+using namespace sylow;
+
+// f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
+__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
+k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, const uint8_t* __restrict__ g2,
+         const uint8_t* __restrict__ g2_inf, size_t g2_stride, size_t n, uint8_t* __restrict__ f_out, int raw_out) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // Every thread of the block runs the loop (SY_LOOP_SYNC needs that): out-of-range threads redo the
+  // last item and discard it; infinite pairs are computed on whatever bytes are there and replaced by 1.
+  size_t i = i0 < n ? i0 : n - 1;
+  size_t j = i * g2_stride;
+  bool inf = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[j]);
+  const uint8_t* p = g1 + i * 64;
+  const uint8_t* q = g2 + j * 128;
+  Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
+  if (i0 >= n) return;
+  if (inf) f = fp12_one();
+  if (raw_out)
+    fp12_store_raw(f_out + i * 384, f);
+  else
+    fp12_store(f_out + i * 384, f);
+}
+
+__global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
+k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;  // all threads run the loops (SY_LOOP_SYNC); the surplus is discarded
+  Fp12 f = raw_in ? fp12_load_raw(f_in + i * 384) : fp12_load(f_in + i * 384);
+  final_exponentiation_assign(f);
+  if (i0 >= n) return;
+  fp12_store(gt_out + i * 384, f);
+}
+
+}  // namespace sylow_kernels
+using namespace sylow_kernels;

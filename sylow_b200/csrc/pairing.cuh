@@ -176,10 +176,9 @@ SY_HD_NOINLINE Fp12 glued_miller_loop(const MillerG1* p /* NV + NF */, const Fp2
 }
 
 // ---------------------------------------------------------------------------- final exponentiation
-// fp6.rs:203-209 / fp12.rs:515-522 for e in {1, 2, 3}
-SY_HD_NOINLINE Fp12 fp12_frobenius(const Fp12& a, int e) {
+// fp6.rs:203-209 / fp12.rs:515-522 for e in {1, 2, 3}; r must not alias a
+SY_HD_NOINLINE void fp12_frobenius_to(Fp12& r, const Fp12& a, int e) {
   bool odd = e & 1;
-  Fp12 r;
   const Fp2 c61 = SY_TAB(kFrob6C1)[e], c62 = SY_TAB(kFrob6C2)[e], c12 = SY_TAB(kFrob12C1)[e];
   r.c0.c0 = odd ? fp2_conj(a.c0.c0) : a.c0.c0;
   r.c0.c1 = fp2_mul(odd ? fp2_conj(a.c0.c1) : a.c0.c1, c61);
@@ -187,6 +186,10 @@ SY_HD_NOINLINE Fp12 fp12_frobenius(const Fp12& a, int e) {
   r.c1.c0 = fp2_mul(odd ? fp2_conj(a.c1.c0) : a.c1.c0, c12);
   r.c1.c1 = fp2_mul(fp2_mul(odd ? fp2_conj(a.c1.c1) : a.c1.c1, c61), c12);
   r.c1.c2 = fp2_mul(fp2_mul(odd ? fp2_conj(a.c1.c2) : a.c1.c2, c62), c12);
+}
+SY_HD Fp12 fp12_frobenius(const Fp12& a, int e) {
+  Fp12 r;
+  fp12_frobenius_to(r, a, e);
   return r;
 }
 
@@ -226,81 +229,89 @@ SY_HD Fp12 cyclotomic_squared(const Fp12& f) {
   return r;
 }
 
-// conj(f^x) with x = BLS_X (pairing.rs:366-392).  The reference walks 256 exponent bits one at a time; the
-// value f^x is the same for any addition chain, so this uses the width-4 NAF of x (63 digits, 14 of them
-// non-zero, digits +-1 .. +-7): 62 + 1 cyclotomic squarings and 13 + 3 multiplications instead of 62 + 27.  Negative
-// digits multiply by the conjugate, which is the inverse on the cyclotomic subgroup f lives in.
-#ifndef SY_EXP_WNAF4
-#define SY_EXP_WNAF4 1
-#endif
-SY_HD_NOINLINE Fp12 exp_by_neg_z(const Fp12& f) {
-#if SY_EXP_WNAF4
-  // width-4 NAF: odd powers f, f^3, f^5, f^7 (one squaring, three products) and 13 products in the ladder
-  Fp12 tab[4], tabc[4];
+// f <- conj(f^x) with x = BLS_X (pairing.rs:366-392), in place.  The reference walks 256 exponent bits one at a time;
+// the value f^x is the same for any addition chain, so this uses the width-4 NAF of x (63 digits, 14 of them non-zero,
+// digits +-1 .. +-7): 62 + 1 cyclotomic squarings and 13 + 3 multiplications instead of 62 + 27.  A negative digit
+// multiplies by the conjugate (the inverse on the cyclotomic subgroup f lives in) through fp12_mul_assign's flag, so
+// the table holds only f^3, f^5, f^7 (f itself stays in the caller's slot): 4 Fp12 of frame instead of 10.
+SY_HD_NOINLINE void exp_by_neg_z_assign(Fp12& f) {
+  Fp12 tab[3], res;
+  res = f;
+  cyclotomic_square_assign(res);  // f^2
+  tab[0] = f;
+  fp12_mul_assign(tab[0], res);
+  tab[1] = tab[0];
+  fp12_mul_assign(tab[1], res);
+  tab[2] = tab[1];
+  fp12_mul_assign(tab[2], res);
   {
-    Fp12 f2 = cyclotomic_squared(f);
-    tab[0] = f;
-    for (int i = 1; i < 4; i++) tab[i] = fp12_mul(tab[i - 1], f2);
-    for (int i = 0; i < 4; i++) tabc[i] = fp12_conj(tab[i]);  // the negative digits' factors
+    int i0 = (SY_TAB(kXWnaf4)[0] - 1) >> 1;  // the leading digit is positive
+    res = i0 ? tab[i0 - 1] : f;
   }
-  Fp12 res = tab[(SY_TAB(kXWnaf4)[0] - 1) >> 1];
   for (int i = 1; i < SY_XWNAF4_LEN; i++) {
     SY_LOOP_SYNC();
     cyclotomic_square_assign(res);
     int d = SY_TAB(kXWnaf4)[i];
     if (d != 0) {
-      SY_STEP_SYNC();
-      fp12_mul_assign(res, d > 0 ? tab[(d - 1) >> 1] : tabc[(-d - 1) >> 1]);
+      int idx = ((d > 0 ? d : -d) - 1) >> 1;
+      fp12_mul_assign(res, idx ? tab[idx - 1] : f, d < 0);
     }
   }
-  return fp12_conj(res);
-#else
-  Fp12 f3 = fp12_mul(cyclotomic_squared(f), f);
-  const Fp12 fc = fp12_conj(f), f3c = fp12_conj(f3);  // the negative digits' factors, conjugated once
-  Fp12 res = SY_TAB(kXWnaf3)[0] == 3 ? f3 : f;
-  for (int i = 1; i < SY_XWNAF3_LEN; i++) {
-    SY_LOOP_SYNC();
-    cyclotomic_square_assign(res);
-    int d = SY_TAB(kXWnaf3)[i];
-    if (d != 0) {
-      SY_STEP_SYNC();
-      fp12_mul_assign(res, d == 3 ? f3 : d == -3 ? f3c : d == 1 ? f : fc);
-    }
-  }
-  return fp12_conj(res);
-#endif
+  fp12_conj_assign(res);
+  f = res;
+}
+SY_HD Fp12 exp_by_neg_z(const Fp12& f) {
+  Fp12 r = f;
+  exp_by_neg_z_assign(r);
+  return r;
 }
 
-// pairing.rs:245-492
-SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
+// pairing.rs:245-492, in place.  Five Fp12 slots in all (f and four locals): every product updates one of its factors,
+// Frobenius images go through one scratch slot, and conjugated factors use fp12_mul_assign's flag.
+SY_HD_NOINLINE void final_exponentiation_assign(Fp12& f) {
+  Fp12 A, C, E, G;
   // easy part (:410-415)
   SY_LOOP_SYNC();
-  Fp12 f = fp12_mul(fp12_conj(f0), fp12_inv(f0));
+  A = fp12_inv(f);
+  fp12_conj_assign(f);
+  fp12_mul_assign(f, A);
   SY_LOOP_SYNC();
-  Fp12 inp = fp12_mul(fp12_frobenius(f, 2), f);
-  // hard part (:437-489); the names follow the reference, dead values give their frame slot to later ones
-  Fp12 b, d, e, k, l;
-  {
-    Fp12 a = exp_by_neg_z(inp);
-    b = cyclotomic_squared(a);
-    a = cyclotomic_squared(b);  // c
-    d = fp12_mul(a, b);
-    e = exp_by_neg_z(d);
-    a = cyclotomic_squared(e);
-    Fp12 g = exp_by_neg_z(a);
-    SY_LOOP_SYNC();
-    a = fp12_mul(fp12_conj(g), e);
-    k = fp12_mul(a, fp12_conj(d));
-  }
-  l = fp12_mul(k, b);
+  fp12_frobenius_to(A, f, 2);
+  fp12_mul_assign(f, A);  // f = inp
+  // hard part (:437-489); the comments give the reference's names
+  A = f;
+  exp_by_neg_z_assign(A);         // a
+  cyclotomic_square_assign(A);    // b
+  C = A;
+  cyclotomic_square_assign(C);    // c
+  fp12_mul_assign(C, A);          // d = c b
+  E = C;
+  exp_by_neg_z_assign(E);         // e
+  G = E;
+  cyclotomic_square_assign(G);    // f
+  exp_by_neg_z_assign(G);         // g
   SY_LOOP_SYNC();
-  b = fp12_mul(k, e);
-  d = fp12_mul(inp, b);                 // n
-  e = fp12_mul(fp12_frobenius(l, 1), d);  // p
+  fp12_conj_assign(G);
+  fp12_mul_assign(G, E);          // h = conj(g) e    (:463-465)
+  fp12_mul_assign(G, C, true);    // k = h conj(d)
+  fp12_mul_assign(A, G);          // l = k b
   SY_LOOP_SYNC();
-  b = fp12_mul(fp12_frobenius(k, 2), e);  // r
-  d = fp12_mul(fp12_conj(inp), l);
-  return fp12_mul(fp12_frobenius(d, 3), b);
+  fp12_mul_assign(E, G);          // m = k e
+  fp12_mul_assign(E, f);          // n = inp m
+  fp12_frobenius_to(C, A, 1);
+  fp12_mul_assign(E, C);          // p = frobenius(l, 1) n
+  SY_LOOP_SYNC();
+  fp12_frobenius_to(C, G, 2);
+  fp12_mul_assign(E, C);          // r = frobenius(k, 2) p
+  fp12_mul_assign(A, f, true);    // t = conj(inp) l
+  fp12_frobenius_to(C, A, 3);
+  fp12_mul_assign(E, C);          // frobenius(t, 3) r
+  f = E;
+}
+SY_HD Fp12 final_exponentiation(const Fp12& f0) {
+  Fp12 r = f0;
+  final_exponentiation_assign(r);
+  return r;
 }
 
 
@@ -308,15 +319,11 @@ SY_HD_NOINLINE Fp12 final_exponentiation(const Fp12& f0) {
 // exponentiation output).  The reference runs a 256-digit NAF ladder with Fp12 squarings; the value g^k does
 // not depend on the chain, so this uses fixed 4-bit windows with cyclotomic squarings and no data-dependent
 // control flow.
-#ifndef SY_GT_GLS
-#define SY_GT_GLS 1
-#endif
 SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
   Fp12 tab[16];
   tab[0] = fp12_one();
   tab[1] = g;
   for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? fp12_mul(tab[i - 1], g) : cyclotomic_squared(tab[i >> 1]);
-#if SY_GT_GLS
   // g^p is the Frobenius map and p = mu (mod r), the order of Gt: the G2 decomposition k = sum k_j mu^j (curve.cuh)
   // turns the exponentiation into 17 windows of 4 cyclotomic squarings and 4 multiplications by frobenius^j(tab[d_j]);
   // a negative k_j multiplies by the conjugate (the inverse on the cyclotomic subgroup).
@@ -340,19 +347,6 @@ SY_HD_NOINLINE Fp12 gt_pow(const Fp12& g, const uint32_t* k) {
     }
   }
   return acc;
-#else
-  Fp12 acc = tab[k[7] >> 28];
-  for (int w = 62; w >= 0; w--) {
-    SY_LOOP_SYNC();
-    cyclotomic_square_assign(acc);
-    cyclotomic_square_assign(acc);
-    cyclotomic_square_assign(acc);
-    cyclotomic_square_assign(acc);
-    uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
-    fp12_mul_assign(acc, tab[d]);
-  }
-  return acc;
-#endif
 }
 
 }  // namespace sylow

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <thread>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -11,6 +13,7 @@
 #include "hash.cuh"
 #include "fr.cuh"
 #include "wire.cuh"
+#include "kernels_pairing.cuh"
 
 using namespace sylow;
 
@@ -31,18 +34,6 @@ using namespace sylow;
 #else
 #define SY_SCALAR_MUL proj_scalar_mul
 #endif
-#ifndef SY_MILLER_THREADS
-#define SY_MILLER_THREADS 128
-#endif
-#ifndef SY_MILLER_MINB
-#define SY_MILLER_MINB 2
-#endif
-#ifndef SY_FEXP_THREADS
-#define SY_FEXP_THREADS 384
-#endif
-#ifndef SY_FEXP_MINB
-#define SY_FEXP_MINB 1
-#endif
 #define SY_MUL_THREADS 256
 #ifndef SY_G2_THREADS
 #define SY_G2_THREADS 256
@@ -61,28 +52,6 @@ struct DstPrime {
   uint32_t len;
   int hash_id;  // 0 XMD Keccak-256, 1 XMD SHA-256, 2 XOF SHAKE128
 };
-
-// f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
-__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
-k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, const uint8_t* __restrict__ g2,
-         const uint8_t* __restrict__ g2_inf, size_t g2_stride, size_t n, uint8_t* __restrict__ f_out, int raw_out) {
-  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // Every thread of the block runs the loop (SY_LOOP_SYNC needs that): out-of-range threads redo the
-  // last item and discard it; infinite pairs are computed on whatever bytes are there and replaced by 1.
-  size_t i = i0 < n ? i0 : n - 1;
-  size_t j = i * g2_stride;
-  bool inf = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[j]);
-  const uint8_t* p = g1 + i * 64;
-  const uint8_t* q = g2 + j * 128;
-  Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
-  if (i0 >= n) return;
-  if (inf) f = fp12_one();
-  if (raw_out)
-    fp12_store_raw(f_out + i * 384, f);
-  else
-    fp12_store(f_out + i * 384, f);
-}
-
 
 // coeffs[i] = G2Affine::precompute(g2[i]): 87 triples (c0, c1, c2), 16704 B per point, Montgomery (raw) or canonical
 __global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
@@ -156,16 +125,6 @@ k_glued(const uint8_t* __restrict__ g1v, size_t sv, const uint8_t* __restrict__ 
   Fp12 f = glued_miller_loop<NV, NF>(p, qx, qy, tabs);
   if (i0 >= n) return;
   fp12_store_raw(f_out + i * 384, f);
-}
-
-__global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
-k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
-  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t i = i0 < n ? i0 : n - 1;  // all threads run the loops (SY_LOOP_SYNC); the surplus is discarded
-  Fp12 f = raw_in ? fp12_load_raw(f_in + i * 384) : fp12_load(f_in + i * 384);
-  Fp12 g = final_exponentiation(f);
-  if (i0 >= n) return;
-  fp12_store(gt_out + i * 384, g);
 }
 
 // out[t] = in[t] * in[t + T] * in[t + 2T] * ...   (Montgomery form in and out)
@@ -293,6 +252,37 @@ k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
   fp_store(out + i * 64, r.x);
   fp_store(out + i * 64 + 32, r.y);
   if (out_inf) out_inf[i] = r.inf;
+}
+
+// Batch-verification weights: r_i = first 8 bytes of Keccak-256(seed || LE64(i)), forced odd (never 0).  The seed is
+// the caller's secret randomness, drawn after the batch is fixed.
+struct WeightSeed {
+  uint64_t w[4];
+};
+SY_HD uint64_t batch_weight(const WeightSeed& seed, uint64_t idx) {
+  uint64_t st[25];
+  for (int i = 0; i < 25; i++) st[i] = 0;
+  for (int i = 0; i < 4; i++) st[i] = seed.w[i];
+  st[4] = idx;
+  st[5] = 0x01;                   // Keccak padding after the 40 message bytes ...
+  st[16] = 0x8000000000000000ull; // ... and the last bit of the 136-byte rate
+  keccak_f1600(st);
+  return st[0] | 1ull;
+}
+// proj_out[i] = r_i * pts[i] (projective, Montgomery form), r_i the weight of item first_index + i
+__global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
+k_g1_mul_weight(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf, const __grid_constant__ WeightSeed seed,
+                uint64_t first_index, size_t n, uint8_t* __restrict__ proj_out) {
+  size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = i0 < n ? i0 : n - 1;
+  G1Aff a{fp_load(pts + i * 64), fp_load(pts + i * 64 + 32), pts_inf && pts_inf[i]};
+  G1Proj q = proj_scalar_mul_u64(affine_to_proj(a), batch_weight(seed, first_index + i));
+  if (i0 < n) g1_store_proj(proj_out + i * 96, q);
+}
+// out[i] = the 64-bit weight of item first_index + i (tests)
+__global__ void k_batch_weights(const __grid_constant__ WeightSeed seed, uint64_t first_index, size_t n, uint64_t* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = batch_weight(seed, first_index + i);
 }
 
 __global__ void __launch_bounds__(SY_G2_THREADS, SY_G2_MINB)
@@ -818,6 +808,16 @@ __global__ void k_fp_op(int op, const uint8_t* a, const uint8_t* b, size_t n, ui
     case 2: r = fp_sub(x, y); break;
     case 3: r = fp_inv(x); break;
     case 4: r = fp_halve(x); break;
+    case 6: r = fp_inv_fermat(x); break;  // the Fermat ladder the binary-GCD inversion replaced (cross-check)
+    case 7: {  // quadratic character: (x / p) + 1 in {0, 1, 2} from the Jacobi iteration, +4 if the Fermat form disagrees
+      int j = fp_jacobi(x);
+      Fp l = fp_pow(x, SY_TAB(kPm1h), 252);
+      int e = fp_is_zero(l) ? 0 : fp_eq(l, fp_one()) ? 1 : -1;
+      r = fp_zero();
+      r.l[0] = (uint32_t)(j + 1) + (j != e ? 4u : 0u);
+      if (i0 < n) fp_store_raw(out + i * 32, r);
+      return;
+    }
     case 8:  // raw limbs in and out: 9 a + b and 9 a + b + b mod p for operands <= p (fp_lin9)
     case 9: {
       Fp xr = fp_load_raw(a + i * 32), yr = fp_load_raw(b + i * 32);
@@ -850,26 +850,6 @@ k_fp12_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   fp12_store(out + i * 384, r);
 }
 
-#ifdef SY_ROLE_SYNC
-// EXPERIMENT (not built by default): warps 0-3 of a block run Miller loops, warps 4-7 run final exponentiations of
-// unrelated inputs, so the two warps that share a scheduler execute different code.
-__global__ void __launch_bounds__(256, 1)
-k_fused_experiment(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, size_t n, uint8_t* __restrict__ f_out,
-                   const uint8_t* __restrict__ f_in, uint8_t* __restrict__ gt_out) {
-  unsigned role = threadIdx.x >> 7;
-  size_t i0 = (size_t)blockIdx.x * 128 + (threadIdx.x & 127);
-  size_t i = i0 < n ? i0 : n - 1;
-  if (role == 0) {
-    const uint8_t* p = g1 + i * 64;
-    const uint8_t* q = g2 + i * 128;
-    Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
-    if (i0 < n) fp12_store_raw(f_out + i * 384, f);
-  } else {
-    Fp12 g = final_exponentiation(fp12_load_raw(f_in + i * 384));
-    if (i0 < n) fp12_store(gt_out + i * 384, g);
-  }
-}
-#endif
 
 // Register-resident Montgomery-multiplication throughput probe (the roofline denominator).
 template <int CHAINS>
@@ -925,7 +905,6 @@ __global__ void __launch_bounds__(256, 1) k_tower_probe(int iters, const uint32_
     if (OP == 0) a.c0.c0 = fp2_mul(a.c0.c0, b.c0.c0);
     if (OP == 1) a.c0.c0 = fp2_sqr(a.c0.c0);
     if (OP == 2) a.c0 = fp6_mul(a.c0, b.c0);
-    if (OP == 10) a.c0 = fp6_mul_lazy(a.c0, b.c0);
     if (OP == 3) a = fp12_mul(a, b);
     if (OP == 4) a = fp12_sqr(a);
     if (OP == 5) a = fp12_sparse_mul(a, b.c0.c0, b.c0.c1, b.c0.c2);
@@ -1078,6 +1057,7 @@ struct sylow_b200_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host<->device copies of the chunked host-pointer calls
   cudaStream_t stream2 = nullptr;                      // second compute stream: odd chunks (their tails overlap)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // fork/join of the chunk-interleaved device paths
   int sms = 148;
   int last_cuda = 0;
   uint64_t launches = 0;
@@ -1086,6 +1066,8 @@ struct sylow_b200_ctx {
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
   DevBuf tables, sum0, sum1, proj, msm;
   unsigned glued_attr_mask = 0;
+  // multi-device parent (sylow_b200_create_multi): owns one single-device context per GPU and nothing else
+  std::vector<sylow_b200_ctx*> children;
 };
 
 static int fail_cuda(sylow_b200_ctx* ctx, cudaError_t e) {
@@ -1103,6 +1085,14 @@ static int fail_cuda(sylow_b200_ctx* ctx, cudaError_t e) {
     if (s__ != 0) return s__;      \
   } while (0)
 
+#define ENTER(ctx)                                          \
+  if (!(ctx)) return SYLOW_B200_ERR_ARG;                    \
+  if (!(ctx)->children.empty()) (ctx) = (ctx)->children[0]; \
+  CK(cudaSetDevice((ctx)->device));
+// `_dev` entry points work on one device's memory: they need a single-device context (sylow_b200_device_ctx)
+#define ENTER_DEV(ctx) \
+  if ((ctx) && !(ctx)->children.empty()) return SYLOW_B200_ERR_ARG;
+
 static int reserve(sylow_b200_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return 0;
   if (b.p) CK(cudaFree(b.p));
@@ -1118,6 +1108,8 @@ static int reserve(sylow_b200_ctx* ctx, DevBuf& b, size_t bytes) {
   return 0;
 }
 
+static constexpr size_t sy_gcd(size_t a, size_t b) { return b ? sy_gcd(b, a % b) : a; }
+static constexpr size_t sy_lcm(size_t a, size_t b) { return a / sy_gcd(a, b) * b; }
 static inline unsigned nblocks(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 static inline cudaStream_t pick(sylow_b200_ctx* ctx, void* stream) {
   return stream ? (cudaStream_t)stream : ctx->stream;
@@ -1127,6 +1119,66 @@ static inline cudaStream_t pick(sylow_b200_ctx* ctx, void* stream) {
     (ctx)->launches++;       \
     CK(cudaGetLastError());  \
   } while (0)
+
+// Launch shapes that do not waste the last wave.  Both pairing kernels run one item per thread for several
+// milliseconds, so a batch that is not a whole number of waves (k_miller keeps 256 threads resident per SM,
+// k_final_exp 384) ends with a partly filled wave that takes as long as a full one - at 2^17 items per GPU (a 2^20
+// batch sharded over 8) that is 3.46 and 2.31 waves.  The whole waves are launched as usual; a remainder of less than
+// 0.6 wave is launched separately as one (k_final_exp) or two (k_miller) SMALL blocks per SM, so that every SM works
+// on it at low occupancy - a lone warp per scheduler runs 1.5x (Miller) to 2x (final exponentiation) faster than one of
+// two or three co-resident warps (profiles/r01_overlap_probe.md), and the remainder finishes in that much less time.
+struct WaveSplit {
+  size_t n_main;       // items in whole waves (launched with the kernel's normal block size)
+  size_t n_tail;       // remainder
+  unsigned tail_threads, tail_blocks;
+};
+static WaveSplit wave_split(const sylow_b200_ctx* ctx, size_t n, int threads, int blocks_per_sm) {
+  WaveSplit w{n, 0, 0, 0};
+  const size_t wave = (size_t)ctx->sms * threads * blocks_per_sm;
+  const size_t r = n % wave;
+  static const int mode = [] {
+    const char* v = getenv("SYLOW_B200_TAIL_SPLIT");  // 0 disables (measurement)
+    return v ? atoi(v) : 1;
+  }();
+  if (!mode || r == 0 || r * 10 >= wave * 6) return w;
+  const size_t slots = (size_t)ctx->sms * blocks_per_sm;
+  unsigned t = (unsigned)(((r + slots - 1) / slots + 31) / 32 * 32);
+  if (t > (unsigned)threads) t = threads;
+  w.n_main = n - r;
+  w.n_tail = r;
+  w.tail_threads = t;
+  w.tail_blocks = (unsigned)((r + t - 1) / t);
+  return w;
+}
+static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                         const uint8_t* g2_inf, size_t n, uint8_t* f_out, int raw_out, cudaStream_t s) {
+  const WaveSplit w = wave_split(ctx, n, SY_MILLER_THREADS, SY_MILLER_MINB);
+  if (w.n_main) {
+    k_miller<<<nblocks(w.n_main, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, w.n_main, f_out,
+                                                                              raw_out);
+    LAUNCHED(ctx);
+  }
+  if (w.n_tail) {
+    const size_t o = w.n_main;
+    k_miller<<<w.tail_blocks, w.tail_threads, 0, s>>>(g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128,
+                                                     g2_inf ? g2_inf + o : nullptr, 1, w.n_tail, f_out + o * 384, raw_out);
+    LAUNCHED(ctx);
+  }
+  return 0;
+}
+static int launch_final_exp(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, size_t n, uint8_t* gt_out, cudaStream_t s) {
+  const WaveSplit w = wave_split(ctx, n, SY_FEXP_THREADS, SY_FEXP_MINB);
+  if (w.n_main) {
+    k_final_exp<<<nblocks(w.n_main, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(f, raw_in, w.n_main, gt_out);
+    LAUNCHED(ctx);
+  }
+  if (w.n_tail) {
+    const size_t o = w.n_main;
+    k_final_exp<<<w.tail_blocks, w.tail_threads, 0, s>>>(f + o * 384, raw_in, w.n_tail, gt_out + o * 384);
+    LAUNCHED(ctx);
+  }
+  return 0;
+}
 
 extern "C" {
 
@@ -1141,6 +1193,8 @@ int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device_id);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fail, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_fail, 0, sizeof(int));
@@ -1154,6 +1208,11 @@ int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
 
 int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (!ctx) return SYLOW_B200_ERR_ARG;
+  if (!ctx->children.empty()) {
+    for (sylow_b200_ctx* c : ctx->children) sylow_b200_destroy(c);
+    delete ctx;
+    return 0;
+  }
   cudaSetDevice(ctx->device);
   DevBuf* bufs[] = {&ctx->in_a, &ctx->in_b, &ctx->in_c, &ctx->in_d, &ctx->flag_a,
                     &ctx->flag_b, &ctx->out, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2};
@@ -1170,8 +1229,47 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return 0;
+}
+
+int sylow_b200_create_multi(sylow_b200_ctx** out, const int* device_ids, int n_devices) {
+  if (!out) return SYLOW_B200_ERR_ARG;
+  *out = nullptr;
+  if (!device_ids || n_devices < 1) return SYLOW_B200_ERR_ARG;
+  sylow_b200_ctx* parent = new (std::nothrow) sylow_b200_ctx();
+  if (!parent) return SYLOW_B200_ERR_NOMEM;
+  parent->device = device_ids[0];
+  for (int i = 0; i < n_devices; i++) {
+    sylow_b200_ctx* c = nullptr;
+    int st = sylow_b200_create(&c, device_ids[i]);
+    if (st == 0) {
+      try {
+        parent->children.push_back(c);
+      } catch (...) {
+        sylow_b200_destroy(c);
+        st = SYLOW_B200_ERR_NOMEM;
+      }
+    }
+    if (st != 0) {
+      for (sylow_b200_ctx* d : parent->children) sylow_b200_destroy(d);
+      delete parent;
+      return st;
+    }
+  }
+  *out = parent;
+  return 0;
+}
+int sylow_b200_device_count(const sylow_b200_ctx* ctx) {
+  if (!ctx) return 0;
+  return ctx->children.empty() ? 1 : (int)ctx->children.size();
+}
+sylow_b200_ctx* sylow_b200_device_ctx(sylow_b200_ctx* ctx, int i) {
+  if (!ctx || i < 0) return nullptr;
+  if (ctx->children.empty()) return i == 0 ? ctx : nullptr;
+  return i < (int)ctx->children.size() ? ctx->children[i] : nullptr;
 }
 
 const char* sylow_b200_strerror(int status) {
@@ -1187,38 +1285,77 @@ const char* sylow_b200_strerror(int status) {
     default: return "unknown status";
   }
 }
-int sylow_b200_last_cuda_error(const sylow_b200_ctx* ctx) { return ctx ? ctx->last_cuda : 0; }
-uint64_t sylow_b200_launch_count(const sylow_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sylow_b200_last_cuda_error(const sylow_b200_ctx* ctx) {
+  if (!ctx) return 0;
+  for (const sylow_b200_ctx* c : ctx->children)
+    if (c->last_cuda) return c->last_cuda;
+  return ctx->last_cuda;
+}
+uint64_t sylow_b200_launch_count(const sylow_b200_ctx* ctx) {
+  if (!ctx) return 0;
+  uint64_t t = ctx->launches;
+  for (const sylow_b200_ctx* c : ctx->children) t += c->launches;
+  return t;
+}
 
 // ------------------------------------------------------------------------------- device variants
 int sylow_b200_miller_loop_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                                      const uint8_t* g2_inf, size_t n, uint8_t* f_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n && (!g1 || !g2 || !f_out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
-  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, pick(ctx, stream)>>>(g1, g1_inf, g2, g2_inf, 1, n,
-                                                                                    f_out, 0);
-  LAUNCHED(ctx);
-  return 0;
+  return launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, f_out, 0, pick(ctx, stream));
 }
 
 int sylow_b200_final_exp_batch_dev(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t* gt_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n && (!f || !gt_out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
-  k_final_exp<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, pick(ctx, stream)>>>(f, 0, n, gt_out);
-  LAUNCHED(ctx);
-  return 0;
+  return launch_final_exp(ctx, f, 0, n, gt_out, pick(ctx, stream));
+}
+
+// Miller loops then final exponentiations of one slice on one stream.  The Miller values (Montgomery form) are staged
+// in gt_out itself; the final exponentiation is in place.
+static int pairing_dev_single(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                              const uint8_t* g2_inf, size_t n, uint8_t* gt_out, cudaStream_t s) {
+  CKS(launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, gt_out, 1, s));
+  return launch_final_exp(ctx, gt_out, 1, n, gt_out, s);
+}
+
+// Optional slicing of the device path over the caller's stream and the context's second stream (SYLOW_B200_PAIR_CHUNK =
+// slice size in pairs).  Measured (profiles/r02_pair_chunk_sweep.jsonl): the partly filled last wave of one kernel does
+// NOT usefully overlap the other stream's kernels - a k_final_exp block needs a whole SM's registers and a k_miller
+// block half of them, so the two never share an SM - and slicing only adds wave tails.  Off by default; the tails are
+// handled by the low-occupancy tail launches above instead.
+static size_t pairing_chunk(const sylow_b200_ctx* ctx, size_t n) {
+  static const long env = [] {
+    const char* v = getenv("SYLOW_B200_PAIR_CHUNK");
+    return v ? atol(v) : 0L;
+  }();
+  if (env > 0) return (size_t)env;
+  (void)ctx;
+  return n;  // default: no slicing (the tail launches of launch_miller / launch_final_exp do the work; see below)
 }
 
 int sylow_b200_pairing_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                                  const uint8_t* g2_inf, size_t n, uint8_t* gt_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n && (!g1 || !g2 || !gt_out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
   cudaStream_t s = pick(ctx, stream);
-  // Miller values (Montgomery form) are staged in gt_out itself; the final exponentiation is in place.
-  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, n, gt_out, 1);
-  LAUNCHED(ctx);
-  k_final_exp<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(gt_out, 1, n, gt_out);
-  LAUNCHED(ctx);
+  const size_t chunk = pairing_chunk(ctx, n);
+  if (n <= chunk + chunk / 2 || s == ctx->stream2) return pairing_dev_single(ctx, g1, g1_inf, g2, g2_inf, n, gt_out, s);
+  CK(cudaEventRecord(ctx->ev_fork, s));
+  CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  size_t c = 0;
+  for (size_t off = 0; off < n; c++) {
+    size_t m = n - off <= chunk + chunk / 2 ? n - off : chunk;
+    CKS(pairing_dev_single(ctx, g1 + off * 64, g1_inf ? g1_inf + off : nullptr, g2 + off * 128,
+                           g2_inf ? g2_inf + off : nullptr, m, gt_out + off * 384, (c & 1) ? ctx->stream2 : s));
+    off += m;
+  }
+  CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   return 0;
 }
 
@@ -1252,6 +1389,7 @@ static const uint8_t kOneCanonical[384] = {1};
 
 int sylow_b200_miller_product_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                                   const uint8_t* g2_inf, size_t n, uint8_t* f_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || !f_out || (n && (!g1 || !g2))) return SYLOW_B200_ERR_ARG;
   cudaStream_t s = pick(ctx, stream);
   if (!n) {
@@ -1260,14 +1398,14 @@ int sylow_b200_miller_product_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const 
   }
   CKS(reserve(ctx, ctx->scratch0, n * 384));
   CKS(reserve(ctx, ctx->scratch1, (n / 4 + 1) * 384));
-  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, n, ctx->scratch0.p, 1);
-  LAUNCHED(ctx);
+  CKS(launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, ctx->scratch0.p, 1, s));
   return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n, f_out, 0, s);
 }
 
 int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf,
                                        const uint8_t* g2, const uint8_t* g2_inf, size_t k, size_t n_checks,
                                        uint8_t* ok_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n_checks && !ok_out)) return SYLOW_B200_ERR_ARG;
   if (!n_checks) return 0;
   size_t n = k * n_checks;
@@ -1275,8 +1413,7 @@ int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, c
   cudaStream_t s = pick(ctx, stream);
   if (n) {
     CKS(reserve(ctx, ctx->scratch0, n * 384));
-    k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, n, ctx->scratch0.p, 1);
-    LAUNCHED(ctx);
+    CKS(launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, ctx->scratch0.p, 1, s));
   }
   k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, k, n_checks, ok_out);
   LAUNCHED(ctx);
@@ -1295,6 +1432,7 @@ static int g1_batch_affine(sylow_b200_ctx* ctx, const uint8_t* d_proj, size_t n,
 
 int sylow_b200_g1_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf,
                                 const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* out_inf, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n && (!pts || !scalars || !out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
   uint8_t* proj = nullptr;
@@ -1310,6 +1448,7 @@ int sylow_b200_g1_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const u
 }
 int sylow_b200_g2_mul_batch_dev(sylow_b200_ctx* ctx, const uint8_t* pts, const uint8_t* pts_inf,
                                 const uint8_t* scalars, size_t n, uint8_t* out, uint8_t* out_inf, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n && (!pts || !scalars || !out))) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
   uint8_t* proj = nullptr;
@@ -1365,6 +1504,7 @@ static int hash_launch(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_
     CKS(reserve(ctx, ctx->proj, n * 96));
     proj = ctx->proj.p;
   }
+  CK(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), s));  // the flag reports THIS call's hashes only
   k_hash_to_g1<<<nblocks(n, SY_HASH_THREADS), SY_HASH_THREADS, 0, s>>>(d_msgs, d_offsets, n, dp, negate, d_out,
                                                                      d_out_inf, ctx->d_fail, proj);
   LAUNCHED(ctx);
@@ -1375,6 +1515,7 @@ static int hash_launch(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_
 int sylow_b200_hash_to_g1_batch_dev(sylow_b200_ctx* ctx, const uint8_t* d_msgs, const uint64_t* d_offsets, size_t n,
                                     const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* d_out,
                                     uint8_t* d_out_inf, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n && (!d_offsets || !d_out))) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
@@ -1416,34 +1557,40 @@ extern "C" {
 // G2PreComputed of the generator, computed on the device once per context
 static int ensure_gen_table(sylow_b200_ctx* ctx, cudaStream_t s) {
   if (ctx->d_gen_table) return 0;
-  uint8_t* d_gen = nullptr;
-  CK(cudaMalloc(&d_gen, 128));
-  cudaError_t e = cudaMalloc(&ctx->d_gen_table, SY_TABLE_BYTES);
+  // the field is set only after the table has been computed: a failure on the way leaves it null (and frees both
+  // buffers), so the next call builds it again instead of using an uninitialised table
+  uint8_t *d_gen = nullptr, *d_tab = nullptr;
+  cudaError_t e = cudaMalloc(&d_gen, 128);
+  if (e == cudaSuccess) e = cudaMalloc(&d_tab, SY_TABLE_BYTES);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_gen, kG2GenWords, 128, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    k_g2_precompute<<<1, 32, 0, s>>>(d_gen, 1, d_tab, 1);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (d_gen) cudaFree(d_gen);
   if (e != cudaSuccess) {
-    cudaFree(d_gen);
-    ctx->d_gen_table = nullptr;
+    if (d_tab) cudaFree(d_tab);
     return fail_cuda(ctx, e);
   }
-  CK(cudaMemcpyAsync(d_gen, kG2GenWords, 128, cudaMemcpyHostToDevice, s));
-  k_g2_precompute<<<1, 32, 0, s>>>(d_gen, 1, ctx->d_gen_table, 1);
-  LAUNCHED(ctx);
-  CK(cudaStreamSynchronize(s));
-  CK(cudaFree(d_gen));
+  ctx->d_gen_table = d_tab;
   return 0;
 }
 
 // f[i] = miller(sig_i, G2gen) * miller(-H(m_i), pk_i) for every signature, Montgomery form, in scratch0:
-// one 2-pair glued loop per thread (shared squaring; the generator's lines come from shared memory).
-static int verify_miller_values(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
-                                const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n, const DstPrime& dp,
-                                cudaStream_t s) {
+// one 2-pair glued loop per thread (shared squaring; the generator's lines come from shared memory).  An infinite
+// signature or key makes its pair contribute 1, like pairing() does (pairing.rs:876-886).
+static int verify_miller_values(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_pks_inf, const uint8_t* d_msgs,
+                                const uint64_t* d_offsets, const uint8_t* d_sigs, const uint8_t* d_sigs_inf, size_t n,
+                                const DstPrime& dp, cudaStream_t s) {
   CKS(ensure_gen_table(ctx, s));
   CKS(reserve(ctx, ctx->scratch0, n * 384));
   CKS(reserve(ctx, ctx->scratch2, n * 65 + 64));
   uint8_t* d_hm = ctx->scratch2.p;
   uint8_t* d_hm_inf = d_hm + n * 64;
   CKS(hash_launch(ctx, d_msgs, d_offsets, n, dp, 1, d_hm, d_hm_inf, s));
-  return launch_glued<1, 1>(ctx, d_hm, 1, d_hm_inf, d_pks, nullptr, d_sigs, 1, nullptr, ctx->d_gen_table, n,
+  return launch_glued<1, 1>(ctx, d_hm, 1, d_hm_inf, d_pks, d_pks_inf, d_sigs, 1, d_sigs_inf, ctx->d_gen_table, n,
                             ctx->scratch0.p, s);
 }
 
@@ -1451,13 +1598,13 @@ static int verify_miller_values(sylow_b200_ctx* ctx, const uint8_t* d_pks, const
 // (device).  Tree of strided partial sums in projective coordinates, then one inversion.  Launched <<<1, 1>>>
 // at the end because fp_pow re-converges with __syncthreads().
 static int g1_sum_reduce(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_t* d_inf, size_t n, int negate,
-                         uint8_t* d_out, uint8_t* d_out_inf, cudaStream_t s) {
+                         uint8_t* d_out, uint8_t* d_out_inf, cudaStream_t s, int affine_in = 1) {
   size_t T = n / 8;
   if (T < 1) T = 1;
   if (T > 148 * 512) T = 148 * 512;
   CKS(reserve(ctx, ctx->sum0, T * 96));
   CKS(reserve(ctx, ctx->sum1, (T / 4 + 1) * 96));
-  k_g1_sum_strided<<<nblocks(T, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_pts, d_inf, 1, n, ctx->sum0.p, T);
+  k_g1_sum_strided<<<nblocks(T, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_pts, d_inf, affine_in, n, ctx->sum0.p, T);
   LAUNCHED(ctx);
   uint8_t* cur = ctx->sum0.p;
   uint8_t* nxt = ctx->sum1.p;
@@ -1477,10 +1624,18 @@ static int g1_sum_reduce(sylow_b200_ctx* ctx, const uint8_t* d_pts, const uint8_
   return 0;
 }
 
-int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_msgs,
-                                        const uint64_t* d_offsets, const uint8_t* d_sigs, size_t n,
-                                        const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* d_f_out,
+static bool load_seed(const uint8_t* weight_seed, WeightSeed& ws) {
+  if (!weight_seed) return false;
+  memcpy(ws.w, weight_seed, 32);
+  return true;
+}
+
+int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_pks_inf,
+                                        const uint8_t* d_msgs, const uint64_t* d_offsets, const uint8_t* d_sigs,
+                                        const uint8_t* d_sigs_inf, size_t n, const uint8_t* dst, size_t dst_len,
+                                        int hash_id, const uint8_t* weight_seed, uint64_t first_index, uint8_t* d_f_out,
                                         void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || !d_f_out || (n && (!d_pks || !d_offsets || !d_sigs))) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
@@ -1491,7 +1646,10 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
   }
   // prod_i e(sig_i, G2gen) = e(sum_i sig_i, G2gen): the n signature pairs collapse into ONE Miller loop against
   // the generator (bilinearity; the Gt value after the final exponentiation is the same), so the slice costs
-  // n fused Miller loops (-H(m_i), pk_i), n point additions and one extra loop.
+  // n fused Miller loops (-H(m_i), pk_i), n point additions and one extra loop.  With weights the same identity
+  // holds for r_i sig_i and r_i H(m_i): two 64-bit ladders per signature on top.
+  WeightSeed ws;
+  const bool weighted = load_seed(weight_seed, ws);
   CKS(ensure_gen_table(ctx, s));
   CKS(reserve(ctx, ctx->scratch0, (n + 1) * 384));
   CKS(reserve(ctx, ctx->scratch1, ((n + 1) / 4 + 1) * 384));
@@ -1501,13 +1659,39 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
   uint8_t* d_sum = d_hm + ((n * 65 + 63) / 64) * 64;  // 64 B point + flag
   uint8_t* d_sum_inf = d_sum + 64;
   CKS(hash_launch(ctx, d_msgs, d_offsets, n, dp, 1, d_hm, d_hm_inf, s));
-  k_miller<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(d_hm, d_hm_inf, d_pks, nullptr, 1, n,
-                                                                     ctx->scratch0.p, 1);
-  LAUNCHED(ctx);
-  CKS(g1_sum_reduce(ctx, d_sigs, nullptr, n, 0, d_sum, d_sum_inf, s));
+  if (weighted) {
+    CKS(reserve(ctx, ctx->proj, n * 96));
+    k_g1_mul_weight<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_hm, d_hm_inf, ws, first_index, n, ctx->proj.p);
+    LAUNCHED(ctx);
+    CKS(g1_batch_affine(ctx, ctx->proj.p, n, 0, d_hm, d_hm_inf, s));
+  }
+  CKS(launch_miller(ctx, d_hm, d_hm_inf, d_pks, d_pks_inf, n, ctx->scratch0.p, 1, s));
+  if (weighted) {
+    k_g1_mul_weight<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_sigs, d_sigs_inf, ws, first_index, n,
+                                                                       ctx->proj.p);
+    LAUNCHED(ctx);
+    CKS(g1_sum_reduce(ctx, ctx->proj.p, nullptr, n, 0, d_sum, d_sum_inf, s, 0));
+  } else {
+    CKS(g1_sum_reduce(ctx, d_sigs, d_sigs_inf, n, 0, d_sum, d_sum_inf, s));
+  }
   CKS((launch_glued<0, 1>(ctx, nullptr, 0, nullptr, nullptr, nullptr, d_sum, 1, d_sum_inf, ctx->d_gen_table, 1,
                           ctx->scratch0.p + n * 384, s)));
   return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n + 1, d_f_out, 0, s);
+}
+
+// *failed = 1 if a hash-to-curve of the last hashing `_dev` call enqueued on `stream` hit SvdW's failing square-root
+// check (GroupError::CannotHashToGroup); synchronises the stream and clears the flag.
+int sylow_b200_hash_failed_dev(sylow_b200_ctx* ctx, void* stream, int* failed) {
+  ENTER_DEV(ctx);
+  if (!ctx || !failed) return SYLOW_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick(ctx, stream);
+  int f = 0;
+  CK(cudaMemcpyAsync(&f, ctx->d_fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (f) CK(cudaMemsetAsync(ctx->d_fail, 0, sizeof(int), s));
+  *failed = f;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------- host variants
@@ -1523,16 +1707,12 @@ static int finish(sylow_b200_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
-#define ENTER(ctx)                                \
-  if (!(ctx)) return SYLOW_B200_ERR_ARG;          \
-  CK(cudaSetDevice((ctx)->device));
+
 
 // Host-pointer pairing / Miller-loop batch.  Large batches are cut into chunks of whole waves of both kernels (SMs x
 // 1536 pairs: six Miller-loop waves, four final-exponentiation waves) and pipelined over three streams: the
 // host->device copy of chunk c+1 and the device->host copy of chunk c-1 run under the kernels of chunk c, so the
 // PCIe time of the 576 bytes per pairing disappears from the call.
-static constexpr size_t sy_gcd(size_t a, size_t b) { return b ? sy_gcd(b, a % b) : a; }
-static constexpr size_t sy_lcm(size_t a, size_t b) { return a / sy_gcd(a, b) * b; }
 static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                         const uint8_t* g2_inf, size_t n, uint8_t* out, bool final_exp) {
   const uint8_t *d1i, *d2i;
@@ -1570,7 +1750,7 @@ static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g
     const uint8_t* f2 = d2i ? d2i + off : nullptr;
     uint8_t* o = ctx->out.p + off * 384;
     if (final_exp)
-      rc = sylow_b200_pairing_batch_dev(ctx, ctx->in_a.p + off * 64, f1, ctx->in_b.p + off * 128, f2, m, o, cs);
+      rc = pairing_dev_single(ctx, ctx->in_a.p + off * 64, f1, ctx->in_b.p + off * 128, f2, m, o, cs);
     else
       rc = sylow_b200_miller_loop_batch_dev(ctx, ctx->in_a.p + off * 64, f1, ctx->in_b.p + off * 128, f2, m, o, cs);
     if (rc) break;
@@ -1595,8 +1775,55 @@ static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g
   return 0;
 }
 
+}  // extern "C" (templates need C++ linkage)
+
+// ------------------------------------------------------------------------------- multi-device dispatch
+// A context made by sylow_b200_create_multi shards the batch as contiguous slices [g n / G, (g + 1) n / G), one
+// host thread per GPU driving that GPU's own single-device context.  Per-item outputs land in the
+// caller's buffers directly; product forms combine the G 384-byte partials on the first device.  Nothing throws
+// across the ABI: thread creation failures come back as SYLOW_B200_ERR_NOMEM.
+template <class Fn>
+static int multi_slices(sylow_b200_ctx* ctx, size_t n, Fn fn) {
+  const size_t G = ctx->children.size();
+  std::vector<int> rc(G, 0);
+  try {
+    std::vector<std::thread> th;
+    th.reserve(G);
+    for (size_t g = 0; g < G; g++) {
+      size_t off = g * n / G, m = (g + 1) * n / G - off;
+      if (!m) continue;
+      sylow_b200_ctx* c = ctx->children[g];
+      th.emplace_back([&rc, &fn, c, g, off, m] { rc[g] = fn(c, g, off, m); });
+    }
+    for (std::thread& t : th) t.join();
+  } catch (...) {
+    return SYLOW_B200_ERR_NOMEM;
+  }
+  for (int r : rc)
+    if (r) return r;
+  return 0;
+}
+static inline bool is_multi(const sylow_b200_ctx* ctx) { return ctx && ctx->children.size() > 1; }
+static inline const uint8_t* adv(const uint8_t* p, size_t bytes) { return p ? p + bytes : nullptr; }
+static inline uint8_t* adv(uint8_t* p, size_t bytes) { return p ? p + bytes : nullptr; }
+// messages of the slice [off, off + m): the byte range and offsets rebased to 0
+struct MsgSlice {
+  const uint8_t* msgs;
+  std::vector<uint64_t> offs;
+  MsgSlice(const uint8_t* all, const uint64_t* offsets, size_t off, size_t m) : msgs(all ? all + offsets[off] : nullptr), offs(m + 1) {
+    for (size_t i = 0; i <= m; i++) offs[i] = offsets[off + i] - offsets[off];
+  }
+};
+
+extern "C" {
+
 int sylow_b200_pairing_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                              const uint8_t* g2_inf, size_t n, uint8_t* gt_out) {
+  if (is_multi(ctx) && g1 && g2 && gt_out)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      return sylow_b200_pairing_batch(c, g1 + off * 64, adv(g1_inf, off), g2 + off * 128, adv(g2_inf, off), m,
+                                      gt_out + off * 384);
+    });
   ENTER(ctx);
   if (n && (!g1 || !g2 || !gt_out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
@@ -1605,6 +1832,11 @@ int sylow_b200_pairing_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8
 
 int sylow_b200_miller_loop_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                                  const uint8_t* g2_inf, size_t n, uint8_t* f_out) {
+  if (is_multi(ctx) && g1 && g2 && f_out)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      return sylow_b200_miller_loop_batch(c, g1 + off * 64, adv(g1_inf, off), g2 + off * 128, adv(g2_inf, off), m,
+                                          f_out + off * 384);
+    });
   ENTER(ctx);
   if (n && (!g1 || !g2 || !f_out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
@@ -1613,6 +1845,17 @@ int sylow_b200_miller_loop_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const u
 
 int sylow_b200_miller_product(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                               const uint8_t* g2_inf, size_t n, uint8_t f_out[384]) {
+  if (is_multi(ctx) && g1 && g2 && f_out && n) {
+    const size_t G = ctx->children.size();
+    std::vector<uint8_t> part(G * 384, 0);
+    for (size_t g = 0; g < G; g++) part[g * 384] = 1;  // empty slices contribute 1
+    uint8_t* pp = part.data();
+    CKS(multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t g, size_t off, size_t m) {
+      return sylow_b200_miller_product(c, g1 + off * 64, adv(g1_inf, off), g2 + off * 128, adv(g2_inf, off), m,
+                                       pp + g * 384);
+    }));
+    return sylow_b200_fp12_product(ctx->children[0], pp, G, f_out);
+  }
   ENTER(ctx);
   if (!f_out || (n && (!g1 || !g2))) return SYLOW_B200_ERR_ARG;
   const uint8_t *d1, *d1i, *d2, *d2i;
@@ -1627,6 +1870,10 @@ int sylow_b200_miller_product(sylow_b200_ctx* ctx, const uint8_t* g1, const uint
 }
 
 int sylow_b200_final_exp_batch(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uint8_t* gt_out) {
+  if (is_multi(ctx) && f && gt_out && n >= 4096)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      return sylow_b200_final_exp_batch(c, f + off * 384, m, gt_out + off * 384);
+    });
   ENTER(ctx);
   if (n && (!f || !gt_out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
@@ -1659,6 +1906,11 @@ int sylow_b200_fp12_product(sylow_b200_ctx* ctx, const uint8_t* f, size_t n, uin
 
 int sylow_b200_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                                    const uint8_t* g2_inf, size_t k, size_t n_checks, uint8_t* ok_out) {
+  if (is_multi(ctx) && g1 && g2 && ok_out)
+    return multi_slices(ctx, n_checks, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      return sylow_b200_pairing_check_batch(c, g1 + off * k * 64, adv(g1_inf, off * k), g2 + off * k * 128,
+                                            adv(g2_inf, off * k), k, m, ok_out + off);
+    });
   ENTER(ctx);
   if (n_checks && !ok_out) return SYLOW_B200_ERR_ARG;
   if (!n_checks) return 0;
@@ -1677,6 +1929,12 @@ int sylow_b200_pairing_check_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const
 
 static int mul_host(sylow_b200_ctx* ctx, int g2, const uint8_t* pts, const uint8_t* pts_inf, const uint8_t* scalars,
                     size_t n, uint8_t* out, uint8_t* out_inf) {
+  if (is_multi(ctx) && pts && scalars && out) {
+    const size_t pb = g2 ? 128 : 64;
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      return mul_host(c, g2, pts + off * pb, adv(pts_inf, off), scalars + off * 32, m, out + off * pb, adv(out_inf, off));
+    });
+  }
   ENTER(ctx);
   if (n && (!pts || !scalars || !out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
@@ -1738,6 +1996,12 @@ static int msgs_to_dev(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t*
 
 int sylow_b200_hash_to_g1_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const uint64_t* offsets, size_t n,
                                 const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* out, uint8_t* out_inf) {
+  if (is_multi(ctx) && offsets && out && n)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      MsgSlice ms(msgs, offsets, off, m);
+      return sylow_b200_hash_to_g1_batch(c, ms.msgs, ms.offs.data(), m, dst, dst_len, hash_id, out + off * 64,
+                                         adv(out_inf, off));
+    });
   ENTER(ctx);
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
@@ -1755,7 +2019,14 @@ int sylow_b200_hash_to_g1_batch(sylow_b200_ctx* ctx, const uint8_t* msgs, const 
 }
 
 int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks, const uint8_t* msgs, const uint64_t* offsets,
-                          size_t n, const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* sigs_out) {
+                          size_t n, const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* sigs_out,
+                          uint8_t* sigs_out_inf) {
+  if (is_multi(ctx) && offsets && sks && sigs_out && n)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      MsgSlice ms(msgs, offsets, off, m);
+      return sylow_b200_sign_batch(c, sks + off * 32, ms.msgs, ms.offs.data(), m, dst, dst_len, hash_id,
+                                   sigs_out + off * 64, adv(sigs_out_inf, off));
+    });
   ENTER(ctx);
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
@@ -1767,15 +2038,32 @@ int sylow_b200_sign_batch(sylow_b200_ctx* ctx, const uint8_t* sks, const uint8_t
   CKS(to_dev(ctx, ctx->in_b, sks, n * 32, &dk));
   CKS(reserve(ctx, ctx->scratch2, n * 65));
   CKS(reserve(ctx, ctx->out, n * 64));
+  CKS(reserve(ctx, ctx->flag_b, n));
   CKS(hash_launch(ctx, dm, dof, n, dp, 0, ctx->scratch2.p, ctx->scratch2.p + n * 64, ctx->stream));
-  CKS(sylow_b200_g1_mul_batch_dev(ctx, ctx->scratch2.p, ctx->scratch2.p + n * 64, dk, n, ctx->out.p, nullptr, nullptr));
+  CKS(sylow_b200_g1_mul_batch_dev(ctx, ctx->scratch2.p, ctx->scratch2.p + n * 64, dk, n, ctx->out.p, ctx->flag_b.p,
+                                  nullptr));
   CK(cudaMemcpyAsync(sigs_out, ctx->out.p, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sigs_out_inf) CK(cudaMemcpyAsync(sigs_out_inf, ctx->flag_b.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   return check_hash_fail(ctx);
 }
 
-int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs,
-                                    const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
-                                    size_t dst_len, int hash_id, uint8_t f_out[384]) {
+int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* pks_inf, const uint8_t* msgs,
+                                    const uint64_t* offsets, const uint8_t* sigs, const uint8_t* sigs_inf, size_t n,
+                                    const uint8_t* dst, size_t dst_len, int hash_id, const uint8_t* weight_seed,
+                                    uint64_t first_index, uint8_t f_out[384]) {
+  if (is_multi(ctx) && offsets && pks && sigs && f_out && n) {
+    const size_t G = ctx->children.size();
+    std::vector<uint8_t> part(G * 384, 0);
+    for (size_t g = 0; g < G; g++) part[g * 384] = 1;
+    uint8_t* pp = part.data();
+    CKS(multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t g, size_t off, size_t m) {
+      MsgSlice ms(msgs, offsets, off, m);
+      return sylow_b200_verify_batch_partial(c, pks + off * 128, adv(pks_inf, off), ms.msgs, ms.offs.data(),
+                                             sigs + off * 64, adv(sigs_inf, off), m, dst, dst_len, hash_id,
+                                             weight_seed, first_index + off, pp + g * 384);
+    }));
+    return sylow_b200_fp12_product(ctx->children[0], pp, G, f_out);
+  }
   ENTER(ctx);
   if (!f_out) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
@@ -1785,13 +2073,16 @@ int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, con
     return 0;
   }
   if (!pks || !sigs) return SYLOW_B200_ERR_ARG;
-  const uint8_t *dm, *dpk, *dsg;
+  const uint8_t *dm, *dpk, *dsg, *dpki, *dsgi;
   const uint64_t* dof;
   CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
   CKS(to_dev(ctx, ctx->in_a, pks, n * 128, &dpk));
   CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
+  CKS(to_dev(ctx, ctx->flag_a, pks_inf, n, &dpki));
+  CKS(to_dev(ctx, ctx->flag_b, sigs_inf, n, &dsgi));
   CKS(reserve(ctx, ctx->out, 384));
-  CKS(sylow_b200_verify_batch_partial_dev(ctx, dpk, dm, dof, dsg, n, dst, dst_len, hash_id, ctx->out.p, nullptr));
+  CKS(sylow_b200_verify_batch_partial_dev(ctx, dpk, dpki, dm, dof, dsg, dsgi, n, dst, dst_len, hash_id, weight_seed,
+                                          first_index, ctx->out.p, nullptr));
   CK(cudaMemcpyAsync(f_out, ctx->out.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
   return check_hash_fail(ctx);
 }
@@ -1806,28 +2097,38 @@ int sylow_b200_verify_batch_finish(sylow_b200_ctx* ctx, const uint8_t* partials,
   return 0;
 }
 
-int sylow_b200_verify_batch(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs, const uint64_t* offsets,
-                            const uint8_t* sigs, size_t n, const uint8_t* dst, size_t dst_len, int hash_id, int* ok) {
+int sylow_b200_verify_batch(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* pks_inf, const uint8_t* msgs,
+                            const uint64_t* offsets, const uint8_t* sigs, const uint8_t* sigs_inf, size_t n,
+                            const uint8_t* dst, size_t dst_len, int hash_id, const uint8_t* weight_seed, int* ok) {
   if (!ok) return SYLOW_B200_ERR_ARG;
   uint8_t f[384];
-  CKS(sylow_b200_verify_batch_partial(ctx, pks, msgs, offsets, sigs, n, dst, dst_len, hash_id, f));
+  CKS(sylow_b200_verify_batch_partial(ctx, pks, pks_inf, msgs, offsets, sigs, sigs_inf, n, dst, dst_len, hash_id,
+                                      weight_seed, 0, f));
   return sylow_b200_verify_batch_finish(ctx, f, 1, ok);
 }
 
-int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* msgs, const uint64_t* offsets,
-                           const uint8_t* sigs, size_t n, const uint8_t* dst, size_t dst_len, int hash_id,
-                           uint8_t* ok_out) {
+int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_t* pks_inf, const uint8_t* msgs,
+                           const uint64_t* offsets, const uint8_t* sigs, const uint8_t* sigs_inf, size_t n,
+                           const uint8_t* dst, size_t dst_len, int hash_id, uint8_t* ok_out) {
+  if (is_multi(ctx) && offsets && pks && sigs && ok_out && n)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      MsgSlice ms(msgs, offsets, off, m);
+      return sylow_b200_verify_each(c, pks + off * 128, adv(pks_inf, off), ms.msgs, ms.offs.data(), sigs + off * 64,
+                                    adv(sigs_inf, off), m, dst, dst_len, hash_id, ok_out + off);
+    });
   ENTER(ctx);
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
   if (!n) return 0;
   if (!pks || !sigs || !ok_out) return SYLOW_B200_ERR_ARG;
-  const uint8_t *dm, *dpk, *dsg;
+  const uint8_t *dm, *dpk, *dsg, *dpki, *dsgi;
   const uint64_t* dof;
   CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
   CKS(to_dev(ctx, ctx->in_a, pks, n * 128, &dpk));
   CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
-  CKS(verify_miller_values(ctx, dpk, dm, dof, dsg, n, dp, ctx->stream));
+  CKS(to_dev(ctx, ctx->flag_a, pks_inf, n, &dpki));
+  CKS(to_dev(ctx, ctx->flag_b, sigs_inf, n, &dsgi));
+  CKS(verify_miller_values(ctx, dpk, dpki, dm, dof, dsg, dsgi, n, dp, ctx->stream));
   CKS(reserve(ctx, ctx->out, n));
   k_check_products<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(ctx->scratch0.p, 1, n, ctx->out.p);
   LAUNCHED(ctx);
@@ -1882,6 +2183,7 @@ int sylow_b200_pairing_check_fixed_batch_dev(sylow_b200_ctx* ctx, const uint8_t*
                                              const uint8_t* d_g2_var, const uint8_t* d_g2_var_inf, size_t k_var,
                                              const uint8_t* d_tables, size_t k_fixed, size_t n_checks,
                                              uint8_t* d_ok_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || (n_checks && (!d_g1 || !d_ok_out || !d_tables || (k_var && !d_g2_var)))) return SYLOW_B200_ERR_ARG;
   if (!n_checks) return 0;
   cudaStream_t s = pick(ctx, stream);
@@ -1905,11 +2207,13 @@ int sylow_b200_pairing_check_fixed_batch_dev(sylow_b200_ctx* ctx, const uint8_t*
 }
 
 int sylow_b200_tables_to_device(sylow_b200_ctx* ctx, const uint8_t* coeffs, size_t k, uint8_t* d_tables_out, void* stream) {
+  ENTER_DEV(ctx);
   if (!ctx || !coeffs || !d_tables_out || !k) return SYLOW_B200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CKS(tables_to_dev(ctx, coeffs, k));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpyAsync(d_tables_out, ctx->tables.p, k * SY_TABLE_BYTES, cudaMemcpyDeviceToDevice, pick(ctx, stream)));
+  CK(cudaStreamSynchronize(pick(ctx, stream)));  // ctx->tables is reused by the next call
   return 0;
 }
 
@@ -1952,6 +2256,10 @@ int sylow_b200_g1_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g1, const u
 
 int sylow_b200_g2_validate_batch(sylow_b200_ctx* ctx, const uint8_t* g2, const uint8_t* g2_inf, size_t n,
                                  int8_t* status_out) {
+  if (is_multi(ctx) && g2 && status_out)
+    return multi_slices(ctx, n, [=](sylow_b200_ctx* c, size_t, size_t off, size_t m) {
+      return sylow_b200_g2_validate_batch(c, g2 + off * 128, adv(g2_inf, off), m, status_out + off);
+    });
   ENTER(ctx);
   if (n && (!g2 || !status_out)) return SYLOW_B200_ERR_ARG;
   if (!n) return 0;
@@ -2289,9 +2597,10 @@ int sylow_b200_threshold_aggregate_batch(sylow_b200_ctx* ctx, const uint64_t* id
   return finish(ctx);
 }
 
-int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk, const uint8_t* msgs,
-                                        const uint64_t* offsets, const uint8_t* sigs, size_t n, const uint8_t* dst,
-                                        size_t dst_len, int hash_id, int* ok) {
+int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk, int pk_inf, const uint8_t* msgs,
+                                        const uint64_t* offsets, const uint8_t* sigs, const uint8_t* sigs_inf, size_t n,
+                                        const uint8_t* dst, size_t dst_len, int hash_id, const uint8_t* weight_seed,
+                                        int* ok) {
   ENTER(ctx);
   if (!ok) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
@@ -2301,33 +2610,64 @@ int sylow_b200_verify_batch_same_signer(sylow_b200_ctx* ctx, const uint8_t* pk, 
     return 0;
   }
   if (!pk || !sigs) return SYLOW_B200_ERR_ARG;
-  const uint8_t *dm, *dpk, *dsg;
+  WeightSeed ws;
+  const bool weighted = load_seed(weight_seed, ws);
+  const uint8_t *dm, *dpk, *dsg, *dsgi;
   const uint64_t* dof;
   CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
   CKS(to_dev(ctx, ctx->in_a, pk, 128, &dpk));
   CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
-  // e(sum sig_i, G2gen) * e(-sum H(m_i), pk) == 1: two Miller loops for the whole batch
+  CKS(to_dev(ctx, ctx->flag_b, sigs_inf, n, &dsgi));
+  // e(sum r_i sig_i, G2gen) * e(-sum r_i H(m_i), pk) == 1 (r_i = 1 without a seed): two Miller loops for the whole batch
   CKS(reserve(ctx, ctx->scratch2, n * 65 + 64));
   CKS(reserve(ctx, ctx->out, 1024));
   uint8_t* d_pairs = ctx->out.p;        // two G1 points (128 B) + two flags at +128 + the G2 pair at +256
   uint8_t* d_flags = ctx->out.p + 128;
   uint8_t* d_g2 = ctx->out.p + 256;     // G2gen || pk
+  uint8_t* d_g2_inf = ctx->out.p + 520; // 0, pk_inf
   uint8_t* d_ok = ctx->out.p + 512;
   uint8_t* d_hm = ctx->scratch2.p;
-  CKS(hash_launch(ctx, dm, dof, n, dp, 0, d_hm, d_hm + n * 64, ctx->stream));
-  CKS(g1_sum_reduce(ctx, dsg, nullptr, n, 0, d_pairs, d_flags, ctx->stream));
-  CKS(g1_sum_reduce(ctx, d_hm, d_hm + n * 64, n, 1, d_pairs + 64, d_flags + 1, ctx->stream));
-  CK(cudaMemcpyAsync(d_g2, kG2GenWords, 128, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_g2 + 128, dpk, 128, cudaMemcpyDeviceToDevice, ctx->stream));
-  CKS(sylow_b200_pairing_check_batch_dev(ctx, d_pairs, d_flags, d_g2, nullptr, 2, 1, d_ok, nullptr));
+  cudaStream_t st_ = ctx->stream;
+  CKS(hash_launch(ctx, dm, dof, n, dp, 0, d_hm, d_hm + n * 64, st_));
+  if (weighted) {
+    CKS(reserve(ctx, ctx->proj, n * 96));
+    k_g1_mul_weight<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, st_>>>(dsg, dsgi, ws, 0, n, ctx->proj.p);
+    LAUNCHED(ctx);
+    CKS(g1_sum_reduce(ctx, ctx->proj.p, nullptr, n, 0, d_pairs, d_flags, st_, 0));
+    k_g1_mul_weight<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, st_>>>(d_hm, d_hm + n * 64, ws, 0, n, ctx->proj.p);
+    LAUNCHED(ctx);
+    CKS(g1_sum_reduce(ctx, ctx->proj.p, nullptr, n, 1, d_pairs + 64, d_flags + 1, st_, 0));
+  } else {
+    CKS(g1_sum_reduce(ctx, dsg, dsgi, n, 0, d_pairs, d_flags, st_));
+    CKS(g1_sum_reduce(ctx, d_hm, d_hm + n * 64, n, 1, d_pairs + 64, d_flags + 1, st_));
+  }
+  const uint8_t h_g2_inf[2] = {0, (uint8_t)(pk_inf ? 1 : 0)};
+  CK(cudaMemcpyAsync(d_g2, kG2GenWords, 128, cudaMemcpyHostToDevice, st_));
+  CK(cudaMemcpyAsync(d_g2 + 128, dpk, 128, cudaMemcpyDeviceToDevice, st_));
+  CK(cudaMemcpyAsync(d_g2_inf, h_g2_inf, 2, cudaMemcpyHostToDevice, st_));
+  CKS(sylow_b200_pairing_check_batch_dev(ctx, d_pairs, d_flags, d_g2, d_g2_inf, 2, 1, d_ok, nullptr));
   uint8_t h_ok = 0;
-  CK(cudaMemcpyAsync(&h_ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&h_ok, d_ok, 1, cudaMemcpyDeviceToHost, st_));
   int st = check_hash_fail(ctx);
   *ok = h_ok;
   return st;
 }
 
 // ------------------------------------------------------------------------------- diagnostics
+int sylow_b200_batch_weights(sylow_b200_ctx* ctx, const uint8_t* weight_seed, uint64_t first_index, size_t n,
+                             uint64_t* out) {
+  ENTER(ctx);
+  if (!weight_seed || (n && !out)) return SYLOW_B200_ERR_ARG;
+  if (!n) return 0;
+  WeightSeed ws;
+  load_seed(weight_seed, ws);
+  CKS(reserve(ctx, ctx->out, n * 8));
+  k_batch_weights<<<nblocks(n, 128), 128, 0, ctx->stream>>>(ws, first_index, n, reinterpret_cast<uint64_t*>(ctx->out.p));
+  LAUNCHED(ctx);
+  CK(cudaMemcpyAsync(out, ctx->out.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish(ctx);
+}
+
 int sylow_b200_fp_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   ENTER(ctx);
   if (n && (!a || !b || !out)) return SYLOW_B200_ERR_ARG;
@@ -2356,14 +2696,6 @@ int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, cons
   return finish(ctx);
 }
 
-#ifdef SY_ROLE_SYNC
-int sylow_b200_fused_experiment(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* f_out,
-                                const uint8_t* f_in, uint8_t* gt_out, void* stream) {
-  k_fused_experiment<<<nblocks(n, 128), 256, 0, pick(ctx, stream)>>>(g1, g2, n, f_out, f_in, gt_out);
-  LAUNCHED(ctx);
-  return 0;
-}
-#endif
 
 int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms_out,
                           double* ops_out) {
@@ -2401,7 +2733,6 @@ int sylow_b200_imad_probe(sylow_b200_ctx* ctx, int variant, int blocks, int thre
       case 37: k_tower_probe<7><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 26; break;
       case 38: k_tower_probe<8><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 4; break;
       case 39: k_tower_probe<9><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 2; break;
-      case 44: k_tower_probe<10><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 18; break;
       case 40: k_overlap_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
       case 41: k_overlap_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;
       case 42: k_overlap_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, src, sink); per_thread_iter = 1; break;

@@ -6,29 +6,10 @@
 #pragma once
 #include "fp.cuh"
 
-// SY_SMALL_CODE=1 keeps the cheap Fp2 operations (add/sub/double/negate/halve/xi) out of line too, which
-// shrinks the hot instruction footprint of the pairing kernels several-fold (profiles/: the dominant
-// stall of the fully inlined build was instruction fetch).
-#ifndef SY_LAZY_FP2
-#define SY_LAZY_FP2 1
-#endif
-#ifndef SY_SMALL_CODE
-#define SY_SMALL_CODE 0
-#endif
-// SY_FORCE_INLINE_FP2=1 inlines the Fp2 product/square into their callers (bigger scheduling regions)
-#ifndef SY_FORCE_INLINE_FP2
-#define SY_FORCE_INLINE_FP2 0
-#endif
-#if SY_FORCE_INLINE_FP2
-#define SY_HD_MUL2 SY_HD
-#else
+// The Fp2 product and square stay out of line (one copy per kernel: the hot instruction footprint is what the
+// instruction caches see); the Fp2 additions are inlined into their callers.
 #define SY_HD_MUL2 SY_HD_NOINLINE
-#endif
-#if SY_SMALL_CODE
-#define SY_HD_ADD SY_HD_NOINLINE
-#else
 #define SY_HD_ADD SY_HD
-#endif
 
 namespace sylow {
 
@@ -61,33 +42,17 @@ SY_HD Fp2 fp2_select(bool c, const Fp2& a, const Fp2& b) {
 SY_HD_ADD Fp2 fp2_halve(const Fp2& a) { return Fp2{fp_halve(a.c0), fp_halve(a.c1)}; }
 
 // (a0 + a1 u)(9 + u) = (9 a0 - a1) + (a0 + 9 a1) u    (fp2.rs:99-107)
-#ifndef SY_XI_LIN9
-#define SY_XI_LIN9 1
-#endif
 SY_HD_ADD Fp2 fp2_mul_xi(const Fp2& a) {
-#if SY_XI_LIN9
   return Fp2{fp_lin9(a.c0, fp_neg_nr(a.c1)), fp_lin9(a.c1, a.c0)};
-#else
-  Fp t0 = fp_mul9(a.c0), t1 = fp_mul9(a.c1);
-  return Fp2{fp_sub(t0, a.c1), fp_add(t1, a.c0)};
-#endif
 }
 // t + xi a and t - xi a: the addition rides in the same reduction
 SY_HD_ADD Fp2 fp2_mul_xi_add(const Fp2& a, const Fp2& t) {
-#if SY_XI_LIN9
   return Fp2{fp_lin9(a.c0, fp_neg_nr(a.c1), t.c0), fp_lin9(a.c1, a.c0, t.c1)};
-#else
-  return fp2_add(fp2_mul_xi(a), t);
-#endif
 }
 SY_HD_ADD Fp2 fp2_sub_mul_xi(const Fp2& t, const Fp2& a) {
-#if SY_XI_LIN9
   // (t0 - 9 a0 + a1, t1 - 9 a1 - a0) = (9 (p - a0) + a1 + t0, 9 (p - a1) + (p - a0) + t1)
   Fp n0 = fp_neg_nr(a.c0), n1 = fp_neg_nr(a.c1);
   return Fp2{fp_lin9(n0, a.c1, t.c0), fp_lin9(n1, n0, t.c1)};
-#else
-  return fp2_sub(t, fp2_mul_xi(a));
-#endif
 }
 
 // Karatsuba with lazy reduction: 3 full 512-bit products, the linear combinations on the unreduced
@@ -100,16 +65,12 @@ SY_HD_ADD Fp2 fp2_sub_mul_xi(const Fp2& t, const Fp2& a) {
 // (about 50 LOP3 set/test instructions per Fp2 product).  Two chains per warp already saturate the multiplier
 // pipe, so the products and the reductions are ordered by empty asm statements that make the next one's first
 // operand depend on the previous one's last limb.
-#ifndef SY_CHAIN_FENCE
-#define SY_CHAIN_FENCE 1
-#endif
-#if SY_CHAIN_FENCE && defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)
 #define SY_AFTER(x, y) asm volatile("" : "+r"(x) : "r"(y))
 #else
 #define SY_AFTER(x, y) ((void)0)
 #endif
 SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
-#if SY_LAZY_FP2
   uint32_t t0[16], t1[16], t2[16], sa[8], sb[8], a1[8];
   fp_mul_wide(t0, a.c0.l, b.c0.l);
 #pragma unroll
@@ -129,19 +90,12 @@ SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
   SY_AFTER(t2[0], r.c0.l[7]);
   r.c1 = fp_redc_wide(t2);
   return r;
-#else
-  Fp t0 = fp_mul(a.c0, b.c0);
-  Fp t1 = fp_mul(a.c1, b.c1);
-  Fp s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
-  return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(s, t0), t1)};
-#endif
 }
 
 // fp2.rs:164-171: ((a0+a1)(a0-a1), 2 a0 a1).  The factors a0+a1 and a0-a1+p are left unreduced
 // (< 2p each, product < 4p^2 < p*R, which is all fp_mul needs) and 2 a0 a1 is doubled before its single
 // reduction (2 a0 a1 < 2p^2 < p*R).
 SY_HD_MUL2 Fp2 fp2_sqr(const Fp2& a) {
-#if SY_LAZY_FP2
   Fp s, d, pp;
 #pragma unroll
   for (int i = 0; i < 8; i++) pp.l[i] = SY_TAB(kP)[i];
@@ -155,11 +109,6 @@ SY_HD_MUL2 Fp2 fp2_sqr(const Fp2& a) {
   r.c0 = fp_mul(s, d);
   r.c1 = fp_redc_wide(t);
   return r;
-#else
-  Fp t = fp_mul(a.c0, a.c1);
-  Fp s = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
-  return Fp2{s, fp_dbl(t)};
-#endif
 }
 
 // FieldExtension::scale by a base-field element (extensions.rs:86-94)
@@ -185,108 +134,6 @@ SY_HD Fp6 fp6_dbl(const Fp6& a) { return Fp6{fp2_dbl(a.c0), fp2_dbl(a.c1), fp2_d
 // multiplication by v (fp6.rs:189-191)
 SY_HD Fp6 fp6_mul_v(const Fp6& a) { return Fp6{fp2_mul_xi(a.c2), a.c0, a.c1}; }
 SY_HD bool fp6_eq(const Fp6& a, const Fp6& b) { return fp2_eq(a.c0, b.c0) & fp2_eq(a.c1, b.c1) & fp2_eq(a.c2, b.c2); }
-
-// ---- unreduced Fp2 values: (re, im) as 512-bit integers mod 2^512, congruent to the true value mod p ------------
-struct alignas(16) Wide2 {
-  uint32_t c0[16], c1[16];
-};
-// Karatsuba product without any reduction.  Coefficients of a and b may be unreduced sums (< 2p):
-//   c1 = a0 b1 + a1 b0 in [0, 2 p^2) ([0, 8 p^2) for sums);  c0 = a0 b0 - a1 b1 in (-p^2, p^2) ((-4, 4) p^2), WRAPPED mod 2^512
-// (inlined into fp6_mul_lazy: the 512-bit values have to stay in registers - staged through local memory the scheme
-// loses more on L1 traffic than it saves on reductions, profiles/r01_lazy_fp6.md)
-SY_HD void fp2_mul_unr(Wide2& r, const Fp2& a, const Fp2& b) {
-  uint32_t t1[16], sa[8], sb[8];
-  fp_mul_wide(r.c0, a.c0.l, b.c0.l);
-  fp_mul_wide(t1, a.c1.l, b.c1.l);
-  fp_add_nr(sa, a.c0.l, a.c1.l);
-  fp_add_nr(sb, b.c0.l, b.c1.l);
-  fp_mul_wide(r.c1, sa, sb);
-  wide_sub(r.c1, r.c0);
-  wide_sub(r.c1, t1);
-  wide_sub(r.c0, t1);
-}
-SY_HD void wide2_add(Wide2& a, const Wide2& b) {
-  wide_add(a.c0, b.c0);
-  wide_add(a.c1, b.c1);
-}
-SY_HD void wide2_sub(Wide2& a, const Wide2& b) {
-  wide_sub(a.c0, b.c0);
-  wide_sub(a.c1, b.c1);
-}
-// both coefficients through the Montgomery reduction; S0 / S1 = conditional subtractions the high halves need
-template <int S0, int S1>
-SY_HD Fp2 fp2_redc(const Wide2& t) {
-  return Fp2{fp_redc_fat<S0>(t.c0), fp_redc_fat<S1>(t.c1)};
-}
-// coefficient-wise sum without reduction (< 2p for canonical inputs)
-SY_HD Fp2 fp2_add_nr(const Fp2& a, const Fp2& b) {
-  Fp2 r;
-  fp_add_nr(r.c0.l, a.c0.l, b.c0.l);
-  fp_add_nr(r.c1.l, a.c1.l, b.c1.l);
-  return r;
-}
-
-// Measured (profiles/r01_lazy_fp6.md): +6 % on an isolated fp12_sqr, nothing on k_miller, so it is off by default.
-#ifndef SY_LAZY_FP6
-#define SY_LAZY_FP6 0
-#endif
-
-// Karatsuba with lazy reduction above Fp2: the six products stay unreduced and the linear combinations are formed on
-// the 512-bit values, so the product needs 8 Montgomery reductions instead of 12 and no reduced Fp2 additions except
-// the last one.  Bounds in units of p^2 (2^512 = 27.98, p 2^256 = 5.29, one offset unit p 2^253 = 0.661), inputs
-// canonical (the bounds are on the Montgomery representatives, all < p):
-//   V_i = a_i b_i:            re in (-1, 1),  im in [0, 2)
-//   a_i b_j + a_j b_i:        re in (-2, 2),  im in [0, 4)
-//   c2 = a0 b2 + a2 b0 + V1:           re (-3, 3) + 5 units -> (0.3, 6.3);     im [0, 6)        one conditional subtraction
-//   c1 = a0 b1 + a1 b0 + xi V2:        re (-13, 11) + 20 units -> (0.2, 24.3); im (-1, 23) + 2 units -> (0.3, 24.4)   three
-//   c0 = V0 + xi (a1 b2 + a2 b1):      9 * 4 p^2 does not fit, so W = a1 b2 + a2 b1 (re + 4 units < 4.7, im < 4) and V0
-//                                      (re + 2 units < 2.4) are reduced separately and xi is applied to the reduced W.
-// With -DSY_LAZY_FP6=1 fp12_sqr (the Miller loop) uses it.  The final exponentiation keeps the compact fp6_mul below in
-// any case: with this 76 KB body next to the cyclotomic squaring its instruction working set no longer fits (-9 %).
-SY_HD_NOINLINE Fp6 fp6_mul_lazy(const Fp6& a, const Fp6& b) {
-  Wide2 v0, v1, v2, m;
-  Fp6 r;
-  fp2_mul_unr(v0, a.c0, b.c0);
-  fp2_mul_unr(v1, a.c1, b.c1);
-  fp2_mul_unr(v2, a.c2, b.c2);
-  // c0
-  fp2_mul_unr(m, fp2_add_nr(a.c1, a.c2), fp2_add_nr(b.c1, b.c2));
-  wide2_sub(m, v1);
-  wide2_sub(m, v2);
-  wide_add_off(m.c0, SY_TAB(kWideOff4));
-  Fp2 w = fp2_redc<0, 0>(m);
-  m = v0;
-  wide_add_off(m.c0, SY_TAB(kWideOff2));
-  r.c0 = fp2_mul_xi_add(w, fp2_redc<0, 0>(m));
-  // c1
-  fp2_mul_unr(m, fp2_add_nr(a.c0, a.c1), fp2_add_nr(b.c0, b.c1));
-  wide2_sub(m, v0);
-  wide2_sub(m, v1);
-  wide_sub(m.c0, v2.c1);   // xi V2 = (9 re2 - im2, 9 im2 + re2)
-  wide_add(m.c1, v2.c0);
-  {
-    uint32_t t[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) t[i] = v2.c0[i];
-    wide_mul9(t);
-    wide_add(m.c0, t);
-#pragma unroll
-    for (int i = 0; i < 16; i++) t[i] = v2.c1[i];
-    wide_mul9(t);
-    wide_add(m.c1, t);
-  }
-  wide_add_off(m.c0, SY_TAB(kWideOff20));
-  wide_add_off(m.c1, SY_TAB(kWideOff2));
-  r.c1 = fp2_redc<3, 3>(m);
-  // c2
-  fp2_mul_unr(m, fp2_add_nr(a.c0, a.c2), fp2_add_nr(b.c0, b.c2));
-  wide2_sub(m, v0);
-  wide2_sub(m, v2);
-  wide2_add(m, v1);
-  wide_add_off(m.c0, SY_TAB(kWideOff5));
-  r.c2 = fp2_redc<1, 1>(m);
-  return r;
-}
 
 // Karatsuba, 6 Fp2 products (value-equal to the 36-product schoolbook of fp6.rs:267-368; this is
 // the form the reference quotes in its own comment at fp6.rs:274-283)
@@ -342,10 +189,13 @@ SY_HD Fp12 fp12_conj(const Fp12& a) { return Fp12{a.c0, fp6_neg(a.c1)}; }
 // The *_assign forms update their first operand in place.  A call like f = fp12_sqr(f) makes the callee write into a
 // hidden temporary that the caller then copies over f (24 + 24 128-bit local loads and stores, each store waiting for
 // its load: 8 % of the final exponentiation's stall samples); with one reference parameter there is no temporary.
-SY_HD_NOINLINE void fp12_mul_assign(Fp12& a, const Fp12& b) {  // b must not alias a
+// conj_b = true multiplies by the conjugate (b.c0, -b.c1) without materialising it (the flag is uniform across the
+// block: exponent digits are compile-time tables):  a conj(b) = (a0 b0 - v a1 b1) + ((a0 + a1)(b0 - b1) - a0 b0 + a1 b1) w.
+SY_HD_NOINLINE void fp12_mul_assign(Fp12& a, const Fp12& b, bool conj_b = false) {  // b must not alias a
   Fp6 t0 = fp6_mul(a.c0, b.c0);
   Fp6 t1 = fp6_mul(a.c1, b.c1);
-  Fp6 s = fp6_mul(fp6_add(a.c0, a.c1), fp6_add(b.c0, b.c1));
+  if (conj_b) t1 = fp6_neg(t1);
+  Fp6 s = fp6_mul(fp6_add(a.c0, a.c1), conj_b ? fp6_sub(b.c0, b.c1) : fp6_add(b.c0, b.c1));
   a.c0 = Fp6{fp2_mul_xi_add(t1.c2, t0.c0), fp2_add(t1.c0, t0.c1), fp2_add(t1.c1, t0.c2)};  // v t1 + t0
   a.c1 = fp6_sub(fp6_sub(s, t0), t1);
 }
@@ -354,18 +204,14 @@ SY_HD Fp12 fp12_mul(const Fp12& a, const Fp12& b) {
   fp12_mul_assign(r, b);
   return r;
 }
+SY_HD void fp12_conj_assign(Fp12& a) { a.c1 = fp6_neg(a.c1); }
 
 // complex squaring (fp12.rs:536-550)
 SY_HD_NOINLINE void fp12_sqr_assign(Fp12& a) {
   Fp6 c0 = fp6_sub(a.c0, a.c1);
   Fp6 c3{fp2_sub_mul_xi(a.c0.c0, a.c1.c2), fp2_sub(a.c0.c1, a.c1.c0), fp2_sub(a.c0.c2, a.c1.c1)};  // a0 - v a1
-#if SY_LAZY_FP6
-  Fp6 c2 = fp6_mul_lazy(a.c0, a.c1);
-  c0 = fp6_add(fp6_mul_lazy(c0, c3), c2);
-#else
   Fp6 c2 = fp6_mul(a.c0, a.c1);
   c0 = fp6_add(fp6_mul(c0, c3), c2);
-#endif
   a.c1 = fp6_dbl(c2);
   a.c0 = Fp6{fp2_mul_xi_add(c2.c2, c0.c0), fp2_add(c2.c0, c0.c1), fp2_add(c2.c1, c0.c2)};  // c0 + v c2
 }

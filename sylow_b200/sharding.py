@@ -56,17 +56,21 @@ def _world(group=None) -> Tuple[int, int]:
 
 
 def verify_batch_sharded(engine, pks: np.ndarray, msgs: Tuple[np.ndarray, np.ndarray], sigs: np.ndarray,
-                         dst: Optional[bytes] = None, device=None, group=None) -> bool:
-    """BLS batch verification of the WHOLE batch (every rank passes the same arrays, or at least its own
-    slice's rows at the right positions): each rank runs hash-to-curve + 2 Miller loops per signature on
-    its slice and reduces them to one Fp12; the partials are all-gathered and every rank finishes with one
-    product + one final exponentiation (redundantly, so all ranks return the verdict)."""
+                         dst: Optional[bytes] = None, device=None, group=None, weight_seed=None) -> bool:
+    """The BLS product check prod e(r_i sig_i, G2gen) e(-r_i H(m_i), pk_i) == 1 over the WHOLE batch (every rank
+    passes the same arrays, or at least its own slice's rows at the right positions): each rank runs hash-to-curve +
+    the Miller loops of its slice and reduces them to one Fp12; the partials are all-gathered and every rank finishes
+    with one product + one final exponentiation (redundantly, so all ranks return the verdict).
+    weight_seed=None is the reference example's unweighted (aggregate) check; with 32 random bytes - the SAME on every
+    rank - it is batch verification with per-signature random weights indexed by the global position."""
     rank, world = _world(group)
     buf, offs = msgs
     n = offs.size - 1
     sl = rank_slice(n, rank, world)
     sbuf, soffs = slice_messages(buf, offs, sl)
     kw = {} if dst is None else {"dst": dst}
+    if weight_seed is not None:
+        kw.update(weight_seed=weight_seed, first_index=sl.start)
     partial = engine.verify_batch_partial(pks[sl], (sbuf, soffs), sigs[sl], **kw)
     return engine.verify_batch_finish(all_gather_partials(partial, device, group))
 

@@ -323,13 +323,14 @@ class KeyPair:
 
 def sign(k: int, msg: bytes) -> G1Affine:
     """lib.rs:179-187"""
-    out = engine().sign_batch(_arr(_fp(int(k) % (1 << 256)), 32), [bytes(msg)])
-    return _g1_from(out[0], 0)
+    out, inf = engine().sign_batch(_arr(_fp(int(k) % (1 << 256)), 32), [bytes(msg)], return_inf=True)
+    return _g1_from(out[0], int(inf[0]))
 
 
 def verify(pubkey: G2Affine, msg: bytes, sig: G1Affine) -> bool:
     """lib.rs:223-236"""
-    if pubkey.infinity or sig.infinity:  # pairing() maps an infinite input to the identity (pairing.rs:876-886)
-        return pubkey.infinity and sig.infinity
-    ok = engine().verify_each(_arr(pubkey._b(), 128), [bytes(msg)], _arr(sig._b(), 64))
+    # an infinite key or signature makes its side's pairing the identity (pairing.rs:876-886): the library applies
+    # that rule itself from the infinity flags
+    ok = engine().verify_each(_arr(pubkey._b(), 128), [bytes(msg)], _arr(sig._b(), 64),
+                              pks_inf=[int(pubkey.infinity)], sigs_inf=[int(sig.infinity)])
     return bool(ok[0])

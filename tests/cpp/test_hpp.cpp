@@ -2,6 +2,7 @@
 // compares with the golden vectors / the oracle.  Reads like the reference's own tests
 // (src/pairing.rs:1052-1072,1101-1120).
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/sylow_b200.hpp"
 
@@ -14,7 +15,8 @@ static void print_fp12(const char* tag, const Fp12& f) {
   std::printf("\n");
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int n_gpus = argc > 1 ? std::atoi(argv[1]) : 1;
   try {
     Engine eng(0);
     G1Affine g1{Fp::from_u64(1), Fp::from_u64(2), false};
@@ -43,10 +45,11 @@ int main() {
     Fp k = Fp::from_u64(987654321);
     Gt a = eng.pairing(eng.g1_mul_batch({g1}, {k})[0], g2), b = eng.pairing(g1, eng.g2_mul_batch({g2}, {k})[0]);
     std::printf("BILINEAR %d\n", a == b && !(a == Gt::identity()));
-    // MultiEngine: two contexts (on this box both on GPU 0) must agree with one - contiguous slices, concatenated
-    // results, and the 384-byte partial exchange of verify_batch
-    {
-      MultiEngine multi({0, 0});
+    // MultiEngine (sylow_b200_create_multi): two device slots must agree with one - contiguous slices, concatenated
+    // results, and the 384-byte partial exchange of verify_batch.  Slots {0, 0} share GPU 0; with a second GPU visible
+    // the same checks run on {0, 1}.
+    for (int leg = 0; leg < (n_gpus >= 2 ? 2 : 1); leg++) {
+      MultiEngine multi(leg == 0 ? std::vector<int>{0, 0} : std::vector<int>{0, 1});
       std::vector<G1Affine> ps;
       std::vector<G2Affine> qs;
       std::vector<Fp> ks;
@@ -66,7 +69,15 @@ int main() {
       std::swap(sigs[1], sigs[3]);
       sigs[1] = sigs[0];
       bool bad = multi.verify_batch(pks, msgs, sigs);
-      std::printf("MULTI %d %d %d %d\n", (int)same_gt, (int)same_mul, (int)good, (int)bad);
+      // random-weight batch verification: same verdicts, and the cancelling forgery (sig_0 + D, sig_1 - D) that the
+      // unweighted product accepts is rejected
+      std::array<std::uint8_t, 32> seed{};
+      for (int i = 0; i < 32; i++) seed[i] = (std::uint8_t)(17 * i + 3);
+      std::vector<G1Affine> good_sigs = eng.sign_batch(ks, msgs);
+      bool wgood = multi.verify_batch(pks, msgs, good_sigs, DST(), &seed);
+      bool wbad = multi.verify_batch(pks, msgs, sigs, DST(), &seed);
+      std::printf("MULTI%d %d %d %d %d %d %d %zu\n", leg, (int)same_gt, (int)same_mul, (int)good, (int)bad, (int)wgood,
+                  (int)wbad, multi.size());
     }
     return 0;
   } catch (const Error& e) {

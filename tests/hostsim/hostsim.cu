@@ -23,6 +23,16 @@ void hs_fp_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     case 3: r = fp_inv(x); break;
     case 4: r = fp_halve(x); break;
     case 5: r = fp_mul9(x); break;
+    case 8: r = fp_inv_fermat(x); break;
+    case 7: {  // (x / p) + 1 from the Jacobi iteration; +4 if x^((p-1)/2) disagrees
+      int j = fp_jacobi(x);
+      Fp l = fp_pow(x, SY_TAB(kPm1h), 252);
+      int e = fp_is_zero(l) ? 0 : fp_eq(l, fp_one()) ? 1 : -1;
+      r = fp_zero();
+      r.l[0] = (uint32_t)(j + 1) + (j != e ? 4u : 0u);
+      fp_store_raw(out, r);
+      return;
+    }
     default: r = fp_neg(x);
   }
   fp_store(out, r);
@@ -168,10 +178,10 @@ int hs_svdw_pair(const uint8_t* u0, const uint8_t* u1, uint8_t* out) {
   fp_store(out + 96, y1);
   return ok ? 1 : 0;
 }
-// Fp6 product, classic (lazy = 0) or with lazy reduction above Fp2 (lazy = 1); 192-byte operands
-void hs_fp6_mul(int lazy, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+// Fp6 product; 192-byte operands
+void hs_fp6_mul( const uint8_t* a, const uint8_t* b, uint8_t* out) {
   Fp6 x{fp2_load(a), fp2_load(a + 64), fp2_load(a + 128)}, y{fp2_load(b), fp2_load(b + 64), fp2_load(b + 128)};
-  Fp6 r = lazy ? fp6_mul_lazy(x, y) : fp6_mul(x, y);
+  Fp6 r = fp6_mul(x, y);
   fp2_store(out, r.c0);
   fp2_store(out + 64, r.c1);
   fp2_store(out + 128, r.c2);

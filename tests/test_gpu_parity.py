@@ -365,12 +365,18 @@ def test_cpp_header(kats, tmp_path):
     libdir = os.path.join(root, "sylow_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "cpp", "test_hpp.cpp"), "-o", exe,
                            "-L" + libdir, "-lsylow_b200", "-Wl,-rpath," + libdir, "-pthread"])
-    out = subprocess.check_output([exe], text=True).splitlines()
+    import torch
+
+    n_gpus = torch.cuda.device_count()
+    out = subprocess.check_output([exe, str(n_gpus)], text=True).splitlines()
     tag = {l.split()[0]: l.split()[1:] for l in out}
     assert [int(x, 16) for x in tag["GT"]] == [int(x, 16) for x in kats["gt_generator"]["fp12"]]
     assert tag["IDENT"] == ["1"] and tag["EMPTY"] == ["1"] and tag["BILINEAR"] == ["1"]
     assert tag["VERIFY"] == ["1", "0", "1"]
-    assert tag["MULTI"] == ["1", "1", "1", "0"]  # MultiEngine (one context per GPU): same results, verdict flips
+    # MultiEngine (sylow_b200_create_multi, slots {0, 0}): same results, verdict flips, weighted form agrees
+    assert tag["MULTI0"] == ["1", "1", "1", "0", "1", "0", "2"]
+    if n_gpus >= 2:  # the same on two real devices
+        assert tag["MULTI1"] == ["1", "1", "1", "0", "1", "0", "2"]
     sig = o.proj_to_affine(o.FpOps, o.sign(0x1234567890ABCDEF, (20).to_bytes(4, "big")))
     assert int(tag["SIG"][0], 16) == sig[0]
 
