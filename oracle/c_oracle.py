@@ -40,6 +40,7 @@ def lib():
             subprocess.check_call(["make", "-s", "-B", "-C", HERE])
             _lib = ctypes.CDLL(SO)
         _lib.so_verify_batch.restype = ctypes.c_int
+        _lib.so_verify_batch_glued.restype = ctypes.c_int
     return _lib
 
 
@@ -153,6 +154,15 @@ def verify_batch(pks, msgs, sigs, dst=DST, threads=None) -> bool:
                                       ctypes.c_size_t(len(dst)), threads or cores()))
 
 
+def verify_batch_glued(pks, msgs, sigs, dst=DST, threads=None) -> bool:
+    """The batch form through glued_miller_loop (pairing.rs:970-1022), as the reference's example runs it."""
+    buf, offs = _msgs(msgs)
+    pks, sigs = _c(pks), _c(sigs)
+    n = offs.size - 1
+    return bool(lib().so_verify_batch_glued(_p(pks), _p(buf), _p(offs), _p(sigs), ctypes.c_size_t(n), dst,
+                                            ctypes.c_size_t(len(dst)), threads or cores()))
+
+
 def constants():
     buf = np.zeros(160 + 64 * 24 + 64 * 3, np.uint8)
     lib().so_constants(_p(buf))
@@ -194,3 +204,54 @@ def time_pairings(budget_s: float):
     n = m * reps
     return n / dt, c, "port", ("%d pairings (precompute + Miller loop + final exp, sylow's formulas restated in C, "
                                "4x64 Montgomery), %d worker threads, %.1f s" % (n, c, dt))
+
+
+def _sample_signatures(m: int, seed: int = 2):
+    """m (public key, 32-byte message, signature) triples with distinct signers, made by this oracle."""
+    rs = np.random.RandomState(seed)
+    sks = rs.randint(0, 256, size=(m, 32), dtype=np.uint8)
+    sks[:, 31] &= 0x1F
+    msgs = np.zeros((m, 32), np.uint8)
+    msgs[:, :8] = np.arange(m, dtype=np.uint64).view(np.uint8).reshape(m, 8)
+    msgs[:, 8:] = rs.randint(0, 256, size=(m, 24), dtype=np.uint8)
+    packed = (msgs.reshape(-1).copy(), np.arange(m + 1, dtype=np.uint64) * 32)
+    G2 = (10857046999023057135944570762232829481370756359578518086990519993285655852781,
+          11559732032986387107991004021392285783925812861821192530917403151452391805634,
+          8495653923123431417604973247489272438418190587263600148770280649306958101930,
+          4082367875863433681332203403145435568316851327593401208105741076214120093531)
+    g2gen = np.tile(np.frombuffer(b"".join(c.to_bytes(32, "little") for c in G2), dtype=np.uint8), (m, 1))
+    pks, _ = g2_mul_batch(g2gen, sks)
+    sigs = sign_batch(sks, packed)
+    return pks, packed, sigs
+
+
+def _tile_msgs(packed, reps):
+    buf, offs = packed
+    m = offs.size - 1
+    return np.tile(buf, reps), np.arange(m * reps + 1, dtype=np.uint64) * 32
+
+
+def time_verifies(budget_s: float, batch_form: bool):
+    """verifies/s of the CPU restatement with one worker per host core on a bounded sample.
+    batch_form=False: `verify` per signature (hash-to-curve + two full pairings, src/lib.rs:223-236).
+    batch_form=True: the example's batch form (hash + glued Miller loop + ONE final exponentiation per call).
+    Returns (value, cores, kind, sample)."""
+    c = cores()
+    m = 4 * c
+    pks, packed, sigs = _sample_signatures(m)
+    fn = verify_batch_glued if batch_form else verify_each
+    t0 = time.perf_counter()
+    r = fn(pks, packed, sigs, threads=c)
+    dt = time.perf_counter() - t0
+    if not np.all(r):
+        raise RuntimeError("CPU oracle rejected its own signatures")
+    reps = min(512, max(1, int(budget_s / max(dt, 1e-3)) - 1))
+    PK, MS, SG = np.tile(pks, (reps, 1)), _tile_msgs(packed, reps), np.tile(sigs, (reps, 1))
+    t0 = time.perf_counter()
+    r = fn(PK, MS, SG, threads=c)
+    dt = time.perf_counter() - t0
+    n = m * reps
+    what = ("batch form: hash-to-curve + glued Miller loop over (sig_i, G2gen), (-H(m_i), pk_i) with every G2 point "
+            "precomputed + one final exponentiation per call" if batch_form else
+            "verify per signature: hash-to-curve + two full pairings")
+    return n / dt, c, "port", "%d signatures (%s; sylow's formulas restated in C), %d worker threads, %.1f s" % (n, what, c, dt)

@@ -182,6 +182,28 @@ def main():
     assert len(k["xof_shake128_short"]["vectors"]) == 3 and len(k["xof_shake128_long_dst"]["vectors"]) == 3
     assert len(xof_dst_long) > 255
 
+    # --- SvdW map vectors from the reference's own Sage specification (src/sage_reference/svdw.sage:1-137), evaluated
+    #     by its plain-Python port oracle/svdw_sage.py (Sage is not in the image; the port restates only the field type).
+    #     The constants the port DERIVES (find_z_svdw, c1..c4) must equal the Rust literals extracted above.
+    import random
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import svdw_sage
+
+    assert os.path.exists(os.path.join(REF, "src", "sage_reference", "svdw.sage"))
+    s = svdw_sage.bn254_g1_svdw()
+    c = k["svdw_constants"]
+    assert (int(s.Z), int(s.c1), int(s.c2), int(s.c3), int(s.c4)) == tuple(int(c[n], 16) for n in ("z", "c1", "c2", "c3", "c4"))
+    rng = random.Random(20261017)
+    us = [0, 1, 2, svdw_sage.P - 1] + [int(z) for z in s.undefs] + [rng.randrange(svdw_sage.P) for _ in range(12)]
+    k["svdw_map_vectors"] = {
+        "source": "src/sage_reference/svdw.sage:87-137 (generic_svdw.map_to_point) via oracle/svdw_sage.py",
+        "provenance": "second, independent pin of the SvdW map: the reference's Sage specification ported to plain "
+                      "Python (Z searched by find_z_svdw, c1..c4 derived), cross-checked on 10^4 random inputs against "
+                      "the restatement of src/svdw.rs by tests/test_svdw_second_pin.py",
+        "cases": [["0x%x" % u, "0x%x" % s.map_to_point(u)[0], "0x%x" % s.map_to_point(u)[1]] for u in us]}
+
     with open(OUT, "w") as f:
         json.dump(k, f, indent=1, sort_keys=True)
     print("wrote", OUT, "with", len(k), "entries")

@@ -105,3 +105,12 @@ def test_hash_sign_verify():
     bad[1] = sigs[0]
     assert c.verify_each(pks, msgs, bad).tolist() == [True, False] + [True] * (len(msgs) - 2)
     assert not c.verify_batch(pks, msgs, bad)
+    # the same batch through glued_miller_loop (shared squarings: the form the reference's example runs, and the
+    # timed CPU arm of bench.py's verify_batch leg); groups of 16 signatures, ragged tail, several threads
+    for t in (1, 3):
+        assert c.verify_batch_glued(pks, msgs, sigs, threads=t)
+        assert not c.verify_batch_glued(pks, msgs, bad, threads=t)
+    pk40, m40, s40 = c._sample_signatures(40)
+    assert c.verify_batch_glued(pk40, m40, s40, threads=2) and c.verify_batch(pk40, m40, s40)
+    s40[39] = s40[0]
+    assert not c.verify_batch_glued(pk40, m40, s40, threads=2)
