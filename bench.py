@@ -576,7 +576,7 @@ def main():
         extras["groth16_4pair_checks_per_s"] = world * nc / (max_over_ranks(ms_g) * 1e-3)
         extras["groth16_checks_per_gpu"] = nc
         extras["groth16_roofline"] = roofline_block(
-            "k_glued<1,3>", "k_glued<1,3> + k_check_products (4-pair glued loop, one final exponentiation per check)", nc,
+            "k_glued", "k_glued<1,3> + k_check_products (4-pair glued loop, one final exponentiation per check)", nc,
             FP_MUL_GROTH16_CHECK, ms_g, peak, analytic, ncu, 4 * 64 + 128 + 1,
             "per check: fused pair 8 444 + 3 table pairs x (6 045 - 63 shared squarings x 36) + final exponentiation 9 202")
         # config #5: variable-base scalar multiplication, 254-bit scalars

@@ -349,4 +349,20 @@ SY_HD_NOINLINE bool hash_to_g1(const uint8_t* msg, size_t msg_len, const uint8_t
   return ok;
 }
 
+// Batch-verification weights: r_i = first 8 bytes of Keccak-256(seed || LE64(i)), forced odd (never 0).  The seed is
+// the caller's secret randomness, drawn after the batch is fixed.
+struct WeightSeed {
+  uint64_t w[4];
+};
+SY_HD uint64_t batch_weight(const WeightSeed& seed, uint64_t idx) {
+  uint64_t st[25];
+  for (int i = 0; i < 25; i++) st[i] = 0;
+  for (int i = 0; i < 4; i++) st[i] = seed.w[i];
+  st[4] = idx;
+  st[5] = 0x01;                   // Keccak padding after the 40 message bytes ...
+  st[16] = 0x8000000000000000ull; // ... and the last bit of the 136-byte rate
+  keccak_f1600(st);
+  return st[0] | 1ull;
+}
+
 }  // namespace sylow

@@ -17,8 +17,22 @@
 #define SY_FEXP_MINB 1
 #endif
 
+// Shared-memory slot of one thread's hot Fp12 accumulator: 384 bytes padded to 400, so that the eight lanes of a
+// 128-bit shared-memory access phase fall into different banks (100 words x lane = 4 x lane mod 32).
+#ifndef SY_MILLER_SMEM
+#define SY_MILLER_SMEM 0
+#endif
+#ifndef SY_FEXP_SMEM
+#define SY_FEXP_SMEM 0
+#endif
+#define SY_ACC_STRIDE 400
+
 namespace sylow_kernels {
 using namespace sylow;
+extern __shared__ uint4 sy_acc_smem[];
+__device__ __forceinline__ Fp12* acc_slot() {
+  return reinterpret_cast<Fp12*>(reinterpret_cast<char*>(sy_acc_smem) + (size_t)threadIdx.x * SY_ACC_STRIDE);
+}
 
 // f_out[i] = miller_loop(g2[i * g2_stride], g1[i]) (Montgomery form if raw_out, else canonical).
 __global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
@@ -32,7 +46,7 @@ k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, con
   bool inf = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[j]);
   const uint8_t* p = g1 + i * 64;
   const uint8_t* q = g2 + j * 128;
-  Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
+  Fp12 f = miller_loop(fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64), SY_MILLER_SMEM ? acc_slot() : nullptr);
   if (i0 >= n) return;
   if (inf) f = fp12_one();
   if (raw_out)
@@ -46,7 +60,7 @@ k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;  // all threads run the loops (SY_LOOP_SYNC); the surplus is discarded
   Fp12 f = raw_in ? fp12_load_raw(f_in + i * 384) : fp12_load(f_in + i * 384);
-  final_exponentiation_assign(f);
+  final_exponentiation_assign(f, SY_FEXP_SMEM ? acc_slot() : nullptr);
   if (i0 >= n) return;
   fp12_store(gt_out + i * 384, f);
 }

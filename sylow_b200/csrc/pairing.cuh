@@ -57,10 +57,13 @@ SY_HD void miller_mul_line(Fp12& f, const Ell& l, const Fp& xp, const Fp& yp) {
 }
 
 // Fused precompute + miller_loop for one (P, Q) pair of finite affine points.
-SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const Fp2& qy) {
+// `acc` (optional) is where the Fp12 accumulator lives during the loop - the kernels pass a shared-memory slot.
+SY_HD_NOINLINE Fp12 miller_loop(const Fp& xp, const Fp& yp, const Fp2& qx, const Fp2& qy, Fp12* acc = nullptr) {
   G2Proj r{qx, qy, fp2_one()};
   Fp2 nqy = fp2_neg(qy);
-  Fp12 f = fp12_one();
+  Fp12 f_local;
+  Fp12& f = acc ? *acc : f_local;
+  f = fp12_one();
   for (int i = 0; i < 64; i++) {
     SY_LOOP_SYNC();
     Ell l = g2_doubling_step(r);
@@ -234,8 +237,9 @@ SY_HD Fp12 cyclotomic_squared(const Fp12& f) {
 // digits +-1 .. +-7): 62 + 1 cyclotomic squarings and 13 + 3 multiplications instead of 62 + 27.  A negative digit
 // multiplies by the conjugate (the inverse on the cyclotomic subgroup f lives in) through fp12_mul_assign's flag, so
 // the table holds only f^3, f^5, f^7 (f itself stays in the caller's slot): 4 Fp12 of frame instead of 10.
-SY_HD_NOINLINE void exp_by_neg_z_assign(Fp12& f) {
-  Fp12 tab[3], res;
+SY_HD_NOINLINE void exp_by_neg_z_assign(Fp12& f, Fp12* acc = nullptr) {
+  Fp12 tab[3], res_local;
+  Fp12& res = acc ? *acc : res_local;  // the running value: the kernels pass a shared-memory slot
   res = f;
   cyclotomic_square_assign(res);  // f^2
   tab[0] = f;
@@ -268,7 +272,7 @@ SY_HD Fp12 exp_by_neg_z(const Fp12& f) {
 
 // pairing.rs:245-492, in place.  Five Fp12 slots in all (f and four locals): every product updates one of its factors,
 // Frobenius images go through one scratch slot, and conjugated factors use fp12_mul_assign's flag.
-SY_HD_NOINLINE void final_exponentiation_assign(Fp12& f) {
+SY_HD_NOINLINE void final_exponentiation_assign(Fp12& f, Fp12* acc = nullptr) {
   Fp12 A, C, E, G;
   // easy part (:410-415)
   SY_LOOP_SYNC();
@@ -280,16 +284,16 @@ SY_HD_NOINLINE void final_exponentiation_assign(Fp12& f) {
   fp12_mul_assign(f, A);  // f = inp
   // hard part (:437-489); the comments give the reference's names
   A = f;
-  exp_by_neg_z_assign(A);         // a
+  exp_by_neg_z_assign(A, acc);    // a
   cyclotomic_square_assign(A);    // b
   C = A;
   cyclotomic_square_assign(C);    // c
   fp12_mul_assign(C, A);          // d = c b
   E = C;
-  exp_by_neg_z_assign(E);         // e
+  exp_by_neg_z_assign(E, acc);    // e
   G = E;
   cyclotomic_square_assign(G);    // f
-  exp_by_neg_z_assign(G);         // g
+  exp_by_neg_z_assign(G, acc);    // g
   SY_LOOP_SYNC();
   fp12_conj_assign(G);
   fp12_mul_assign(G, E);          // h = conj(g) e    (:463-465)

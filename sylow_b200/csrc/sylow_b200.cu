@@ -254,21 +254,6 @@ k_g1_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf,
   if (out_inf) out_inf[i] = r.inf;
 }
 
-// Batch-verification weights: r_i = first 8 bytes of Keccak-256(seed || LE64(i)), forced odd (never 0).  The seed is
-// the caller's secret randomness, drawn after the batch is fixed.
-struct WeightSeed {
-  uint64_t w[4];
-};
-SY_HD uint64_t batch_weight(const WeightSeed& seed, uint64_t idx) {
-  uint64_t st[25];
-  for (int i = 0; i < 25; i++) st[i] = 0;
-  for (int i = 0; i < 4; i++) st[i] = seed.w[i];
-  st[4] = idx;
-  st[5] = 0x01;                   // Keccak padding after the 40 message bytes ...
-  st[16] = 0x8000000000000000ull; // ... and the last bit of the 136-byte rate
-  keccak_f1600(st);
-  return st[0] | 1ull;
-}
 // proj_out[i] = r_i * pts[i] (projective, Montgomery form), r_i the weight of item first_index + i
 __global__ void __launch_bounds__(SY_MUL_THREADS, SY_G1_MINB)
 k_g1_mul_weight(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ pts_inf, const __grid_constant__ WeightSeed seed,

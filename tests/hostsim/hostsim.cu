@@ -178,6 +178,20 @@ int hs_svdw_pair(const uint8_t* u0, const uint8_t* u1, uint8_t* out) {
   fp_store(out + 96, y1);
   return ok ? 1 : 0;
 }
+// batch-verification weight of item idx (hash.cuh) and r * P for a 64-bit r (curve.cuh): the two pieces of the
+// random-weight batch verification that are not covered by the other entry points
+uint64_t hs_batch_weight(const uint8_t* seed32, uint64_t idx) {
+  WeightSeed ws;
+  memcpy(ws.w, seed32, 32);
+  return batch_weight(ws, idx);
+}
+void hs_g1_mul_u64(const uint8_t* g1, uint64_t k, uint8_t* out /* 64 B affine */, uint8_t* out_inf) {
+  G1Aff a{fp_load(g1), fp_load(g1 + 32), false};
+  G1Aff r = proj_to_affine(proj_scalar_mul_u64(affine_to_proj(a), k));
+  fp_store(out, r.x);
+  fp_store(out + 32, r.y);
+  *out_inf = r.inf;
+}
 // Fp6 product; 192-byte operands
 void hs_fp6_mul( const uint8_t* a, const uint8_t* b, uint8_t* out) {
   Fp6 x{fp2_load(a), fp2_load(a + 64), fp2_load(a + 128)}, y{fp2_load(b), fp2_load(b + 64), fp2_load(b + 128)};

@@ -385,3 +385,21 @@ def test_expander_generic(hs, kats):
             out = ctypes.create_string_buffer(ln)
             hs.hs_expand(hid, b"abcdef" * 30, 180, dp, len(dp), ln, out)
             assert out.raw == o.expand_message(b"abcdef" * 30, o.DST, ln, name)
+
+
+def test_batch_weights_and_short_ladder(hs):
+    """The two pieces of random-weight batch verification: r_i = first 8 bytes of Keccak-256(seed || LE64(i)) | 1
+    (hash.cuh) and the 64-bit ladder r * P (curve.cuh), against the oracle's Keccak-256 and scalar multiplication."""
+    hs.hs_batch_weight.restype = ctypes.c_uint64
+    hs.hs_batch_weight.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
+    hs.hs_g1_mul_u64.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_char_p]
+    rng = random.Random(64)
+    seed = bytes(rng.randrange(256) for _ in range(32))
+    for idx in (0, 1, 2, 255, 256, (1 << 32) - 1, 1 << 32, (1 << 64) - 1, rng.randrange(1 << 64)):
+        exp = int.from_bytes(o.keccak256(seed + idx.to_bytes(8, "little"))[:8], "little") | 1
+        assert hs.hs_batch_weight(seed, idx) == exp
+    out, inf = ctypes.create_string_buffer(64), ctypes.create_string_buffer(1)
+    p = w.rand_g1(rng)
+    for k in (1, 2, 15, 16, 17, (1 << 60) - 1, 1 << 60, (1 << 64) - 1, rng.randrange(1 << 64) | 1):
+        hs.hs_g1_mul_u64(w.g1_b(p), k, out, inf)
+        assert w.b_g1(out.raw, inf.raw[0]) == o.proj_to_affine(o.FpOps, o.proj_mul(o.FpOps, o.affine_to_proj(o.FpOps, p), k))

@@ -20,8 +20,8 @@ class OracleEngine:
 
         self.c = c_oracle
 
-    def verify_batch_partial(self, pks, msgs, sigs, dst=None):
-        # prod miller(sig, G2gen) * miller(-H(m), pk) over the slice, via the oracle's primitives
+    def verify_batch_partial(self, pks, msgs, sigs, dst=None, weight_seed=None, first_index=0):
+        # prod miller(r_i sig, G2gen) * miller(-r_i H(m), pk) over the slice, via the oracle's primitives
         c = self.c
         n = msgs[1].size - 1
         if n == 0:
@@ -29,6 +29,15 @@ class OracleEngine:
             one[0] = 1
             return one
         hm, _ = c.hash_to_g1_batch(msgs, threads=1)
+        if weight_seed is not None:
+            from oracle import bn254_py as ob
+
+            r = np.zeros((n, 32), np.uint8)
+            for i in range(n):
+                wt = int.from_bytes(ob.keccak256(bytes(weight_seed) + (first_index + i).to_bytes(8, "little"))[:8], "little") | 1
+                r[i, :8] = np.frombuffer(wt.to_bytes(8, "little"), np.uint8)
+            hm, _ = c.g1_mul_batch(hm, r, threads=1)
+            sigs, _ = c.g1_mul_batch(np.ascontiguousarray(sigs), r, threads=1)
         P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
         neg = hm.copy()
         for i in range(n):
@@ -99,9 +108,23 @@ def _worker(rank, world, port, n, corrupt, q):
             sigs[n - 1] = sigs[0]
         eng = OracleEngine()
         ok = sharding.verify_batch_sharded(eng, pks, (buf, offs), sigs)
+        seed = bytes(range(32))
+        okw = sharding.verify_batch_sharded(eng, pks, (buf, offs), sigs, weight_seed=seed)
+        forged_u = forged_w = None
+        if n >= 2 and not corrupt:
+            # a forgery that cancels ACROSS the two ranks: sig_0 + D on rank 0's slice, sig_(n-1) - D on rank 1's.  The
+            # unweighted product (the reference example's check) accepts it; the weighted form rejects it on every rank.
+            F = o.FpOps
+            D = o.affine_to_proj(F, w.rand_g1(__import__("random").Random(3)))
+            f = sigs.copy()
+            for i, d in ((0, D), (n - 1, o.proj_neg(F, D))):
+                pt = o.proj_to_affine(F, o.proj_add(F, o.affine_to_proj(F, w.b_g1(bytes(sigs[i]))), d))
+                f[i] = np.frombuffer(w.g1_b(pt), np.uint8)
+            forged_u = sharding.verify_batch_sharded(eng, pks, (buf, offs), f)
+            forged_w = sharding.verify_batch_sharded(eng, pks, (buf, offs), f, weight_seed=seed)
         g1 = np.concatenate([sigs, sigs])[:n]
         prod = sharding.miller_product_sharded(eng, g1, pks)
-        q.put((rank, ok, bytes(prod), bytes(c.miller_product(g1, pks, threads=1))))
+        q.put((rank, ok, bytes(prod), bytes(c.miller_product(g1, pks, threads=1)), okw, forged_u, forged_w))
     finally:
         dist.destroy_process_group()
 
@@ -118,9 +141,12 @@ def test_world_size_2_gloo(n, corrupt):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok, prod, ref in res:
+    for rank, ok, prod, ref, okw, forged_u, forged_w in res:
         assert ok is (not corrupt), (rank, ok)
+        assert okw is (not corrupt), (rank, okw)  # random-weight form: same verdict on valid / corrupted batches
         assert prod == ref  # sharded glued product == unsharded, bit for bit
+        if n >= 2 and not corrupt:
+            assert forged_u is True and forged_w is False, (rank, forged_u, forged_w)
 
 
 def test_rank_slice_covers_batch():

@@ -72,18 +72,22 @@ int main(int argc, char** argv) {
   float ms_m = 0, ms_f = 0;
   unsigned gm = (unsigned)((n + SY_MILLER_THREADS - 1) / SY_MILLER_THREADS);
   unsigned gf = (unsigned)((n + SY_FEXP_THREADS - 1) / SY_FEXP_THREADS);
-  k_miller<<<gm, SY_MILLER_THREADS>>>(g1, nullptr, g2, nullptr, 1, n, f, 1);
+  const size_t sm_m = SY_MILLER_SMEM ? (size_t)SY_MILLER_THREADS * SY_ACC_STRIDE : 0;
+  const size_t sm_f = SY_FEXP_SMEM ? (size_t)SY_FEXP_THREADS * SY_ACC_STRIDE : 0;
+  CHECK(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_m));
+  CHECK(cudaFuncSetAttribute(k_final_exp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f));
+  k_miller<<<gm, SY_MILLER_THREADS, sm_m>>>(g1, nullptr, g2, nullptr, 1, n, f, 1);
   CHECK(cudaDeviceSynchronize());
   cudaEventRecord(a);
-  for (int r = 0; r < reps; r++) k_miller<<<gm, SY_MILLER_THREADS>>>(g1, nullptr, g2, nullptr, 1, n, f, 1);
+  for (int r = 0; r < reps; r++) k_miller<<<gm, SY_MILLER_THREADS, sm_m>>>(g1, nullptr, g2, nullptr, 1, n, f, 1);
   cudaEventRecord(b);
   CHECK(cudaDeviceSynchronize());
   cudaEventElapsedTime(&ms_m, a, b);
   unsigned long long cm = checksum(f, n * 384, d_sum);
-  k_final_exp<<<gf, SY_FEXP_THREADS>>>(f, 1, n, gt);
+  k_final_exp<<<gf, SY_FEXP_THREADS, sm_f>>>(f, 1, n, gt);
   CHECK(cudaDeviceSynchronize());
   cudaEventRecord(a);
-  for (int r = 0; r < reps; r++) k_final_exp<<<gf, SY_FEXP_THREADS>>>(f, 1, n, gt);
+  for (int r = 0; r < reps; r++) k_final_exp<<<gf, SY_FEXP_THREADS, sm_f>>>(f, 1, n, gt);
   cudaEventRecord(b);
   CHECK(cudaDeviceSynchronize());
   cudaEventElapsedTime(&ms_f, a, b);
