@@ -410,8 +410,12 @@ inline Fp fp_mul(const Fp& a, const Fp& b) {
 // (72 IMAD).  An Fp2 product needs 3 wide products and only 2 reductions (tower.cuh), 336 IMAD-pipe
 // instructions instead of 3 * 136.  Inputs of fp_mul_wide may be unreduced sums (< 2^256).
 #if defined(__CUDA_ARCH__)
-// X[0..7] += (a0,a1,a2,a3) * b at limb pairs (0,1),(2,3),(4,5),(6,7); carry out is WRITTEN to X[8]
-__device__ __forceinline__ void wide_row_carry(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+// X[0..7] += (a0,a1,a2,a3) * b at limb pairs (0,1),(2,3),(4,5),(6,7); the carry out (weight 2^256 relative to X[0]) is
+// added into `fold`, the limb of the OTHER accumulator that sits at that weight.  `fold` is always the top limb of a
+// pair that wide_row_top has just written: hi(a7 * b) + carry <= a7, so the addition cannot overflow as long as the
+// multiplicand's top limb is not 0xffffffff (every first operand of fp_mul_wide is below 4p < 2^256 - 2^224).
+__device__ __forceinline__ void wide_row_fold(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b,
+                                              uint32_t& fold) {
   asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
       "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
       "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
@@ -420,48 +424,48 @@ __device__ __forceinline__ void wide_row_carry(uint32_t* X, uint32_t a0, uint32_
       "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
       "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
       "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-      "addc.u32 %8, 0, 0;"
-      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "=r"(X[8])
+      "addc.u32 %8, %8, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(fold)
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
-// X[0..6] += ..., X[7] is fresh (written): the top product's high half plus the final carry
-__device__ __forceinline__ void wide_row_fresh(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+// X[0..5] += ..., the top pair (X[6], X[7]) is fresh (written): the product a3 * b plus the chain's carry
+__device__ __forceinline__ void wide_row_top(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
   asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
       "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
       "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
       "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
       "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
       "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
-      "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, 0;\n\t"
       "madc.hi.u32 %7, %11, %12, 0;"
-      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "=r"(X[7])
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "=r"(X[6]), "=r"(X[7])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
 __device__ __forceinline__ void wide_row_first(uint32_t* X, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
   mul_row4(X, a0, a1, a2, a3, b);
 }
 
-// T = a * b.  E collects the products whose position i+j is even, O (offset by one limb) the others;
-// the row order guarantees that every chain either ends in a fresh limb or hands its carry to one.
+// T = a * b.  E collects the products whose position i+j is even, O (offset by one limb) the others.  For every
+// multiplier limb the row of the odd multiplicand limbs goes first and WRITES its top pair, then the row of the even
+// limbs accumulates below it and folds its carry into that pair's top limb - no carry is ever materialised in a
+// register of its own.  Requires a[7] != 0xffffffff (see wide_row_fold); b is any 256-bit value.
 __device__ __forceinline__ void fp_mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
   uint32_t E[16], O[16];
-  O[15] = 0;
   wide_row_first(E, a[0], a[2], a[4], a[6], b[0]);
   wide_row_first(O, a[1], a[3], a[5], a[7], b[0]);
-  // row 1: a_even * b1 -> O[0..7] (+carry to O[8]); a_odd * b1 -> E[2..9] (E[8] = 0 so far, E[9] fresh)
-  wide_row_carry(O + 0, a[0], a[2], a[4], a[6], b[1]);
-  E[8] = 0;
-  wide_row_fresh(E + 2, a[1], a[3], a[5], a[7], b[1]);
+  // b1: odd limbs -> E[2..9] (E[8], E[9] fresh); even limbs -> O[0..7], carry into E[9]
+  wide_row_top(E + 2, a[1], a[3], a[5], a[7], b[1]);
+  wide_row_fold(O + 0, a[0], a[2], a[4], a[6], b[1], E[9]);
 #pragma unroll
   for (int i = 2; i < 8; i += 2) {
-    // even row i: a_even -> E[i..i+7] (+carry to E[i+8]); a_odd -> O[i..i+7] (O[i+6] holds a carry, O[i+7] fresh)
-    wide_row_carry(E + i, a[0], a[2], a[4], a[6], b[i]);
-    wide_row_fresh(O + i, a[1], a[3], a[5], a[7], b[i]);
-    // odd row i+1: a_even -> O[i..i+7] (+carry to O[i+8]); a_odd -> E[i+2..i+9] (E[i+8] holds a carry, E[i+9] fresh)
-    wide_row_carry(O + i, a[0], a[2], a[4], a[6], b[i + 1]);
-    wide_row_fresh(E + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);
+    // b_i: odd limbs -> O[i..i+7] (top pair fresh); even limbs -> E[i..i+7], carry into O[i+7]
+    wide_row_top(O + i, a[1], a[3], a[5], a[7], b[i]);
+    wide_row_fold(E + i, a[0], a[2], a[4], a[6], b[i], O[i + 7]);
+    // b_(i+1): odd limbs -> E[i+2..i+9] (top pair fresh); even limbs -> O[i..i+7], carry into E[i+9]
+    wide_row_top(E + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);
+    wide_row_fold(O + i, a[0], a[2], a[4], a[6], b[i + 1], E[i + 9]);
   }
-  // T = E + (O << 32); O[15] = 0 and the sum is < 2^512
+  // T = E + (O << 32); O[0..13] are defined, the sum is < 2^512
   T[0] = E[0];
   asm("add.cc.u32 %0, %15, %30;\n\t"
       "addc.cc.u32 %1, %16, %31;\n\t"
@@ -477,13 +481,13 @@ __device__ __forceinline__ void fp_mul_wide(uint32_t* T, const uint32_t* a, cons
       "addc.cc.u32 %11, %26, %41;\n\t"
       "addc.cc.u32 %12, %27, %42;\n\t"
       "addc.cc.u32 %13, %28, %43;\n\t"
-      "addc.u32 %14, %29, %44;"
+      "addc.u32 %14, %29, 0;"
       : "=r"(T[1]), "=r"(T[2]), "=r"(T[3]), "=r"(T[4]), "=r"(T[5]), "=r"(T[6]), "=r"(T[7]), "=r"(T[8]), "=r"(T[9]),
         "=r"(T[10]), "=r"(T[11]), "=r"(T[12]), "=r"(T[13]), "=r"(T[14]), "=r"(T[15])
       : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]),
         "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]),
         "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]),
-        "r"(O[13]), "r"(O[14]));
+        "r"(O[13]));
 }
 
 // One reduce-only CIOS round (mont_round without the a * b_i terms): T = X + Y * 2^32, X[0] -> 0, roles swap.

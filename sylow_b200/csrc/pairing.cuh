@@ -130,14 +130,16 @@ SY_HD void glued_mul_line(Fp12& f, const Ell& l, const MillerG1& p) {
 // (multiplication order differs; Fp12 multiplication is exact and commutative).
 template <int NV, int NF>
 SY_HD_NOINLINE Fp12 glued_miller_loop(const MillerG1* p /* NV + NF */, const Fp2* qx, const Fp2* qy /* NV */,
-                                      const Ell* const* tables /* NF */) {
+                                      const Ell* const* tables /* NF */, Fp12* acc = nullptr) {
   G2Proj r[NV > 0 ? NV : 1];
   Fp2 nqy[NV > 0 ? NV : 1];
   for (int v = 0; v < NV; v++) {
     r[v] = G2Proj{qx[v], qy[v], fp2_one()};
     nqy[v] = fp2_neg(qy[v]);
   }
-  Fp12 f = fp12_one();
+  Fp12 f_local;
+  Fp12& f = acc ? *acc : f_local;  // the kernels pass a shared-memory slot (see miller_loop)
+  f = fp12_one();
   int idx = 0;
   for (int i = 0; i < 64; i++) {
     SY_LOOP_SYNC();

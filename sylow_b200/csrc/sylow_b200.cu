@@ -122,7 +122,11 @@ k_glued(const uint8_t* __restrict__ g1v, size_t sv, const uint8_t* __restrict__ 
     p[NV + t].y = fp_load(a + 32);
     p[NV + t].skip = g1f_inf && g1f_inf[i * sf + t];
   }
-  Fp12 f = glued_miller_loop<NV, NF>(p, qx, qy, tabs);
+  // the accumulator's shared-memory slot sits behind the NF tables (16-byte aligned: 87 * 192 is a multiple of 16)
+  Fp12* acc = SY_MILLER_SMEM ? reinterpret_cast<Fp12*>(reinterpret_cast<char*>(sy_smem) + (size_t)NF * 87 * 192 +
+                                                       (size_t)threadIdx.x * SY_ACC_STRIDE)
+                             : nullptr;
+  Fp12 f = glued_miller_loop<NV, NF>(p, qx, qy, tabs, acc);
   if (i0 >= n) return;
   fp12_store_raw(f_out + i * 384, f);
 }
@@ -1139,14 +1143,15 @@ static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* 
                          const uint8_t* g2_inf, size_t n, uint8_t* f_out, int raw_out, cudaStream_t s) {
   const WaveSplit w = wave_split(ctx, n, SY_MILLER_THREADS, SY_MILLER_MINB);
   if (w.n_main) {
-    k_miller<<<nblocks(w.n_main, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, s>>>(g1, g1_inf, g2, g2_inf, 1, w.n_main, f_out,
-                                                                              raw_out);
+    k_miller<<<nblocks(w.n_main, SY_MILLER_THREADS), SY_MILLER_THREADS, SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS), s>>>(
+        g1, g1_inf, g2, g2_inf, 1, w.n_main, f_out, raw_out);
     LAUNCHED(ctx);
   }
   if (w.n_tail) {
     const size_t o = w.n_main;
-    k_miller<<<w.tail_blocks, w.tail_threads, 0, s>>>(g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128,
-                                                     g2_inf ? g2_inf + o : nullptr, 1, w.n_tail, f_out + o * 384, raw_out);
+    k_miller<<<w.tail_blocks, w.tail_threads, SY_MILLER_SMEM_BYTES(w.tail_threads), s>>>(
+        g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128, g2_inf ? g2_inf + o : nullptr, 1, w.n_tail,
+        f_out + o * 384, raw_out);
     LAUNCHED(ctx);
   }
   return 0;
@@ -1154,12 +1159,14 @@ static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* 
 static int launch_final_exp(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, size_t n, uint8_t* gt_out, cudaStream_t s) {
   const WaveSplit w = wave_split(ctx, n, SY_FEXP_THREADS, SY_FEXP_MINB);
   if (w.n_main) {
-    k_final_exp<<<nblocks(w.n_main, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(f, raw_in, w.n_main, gt_out);
+    k_final_exp<<<nblocks(w.n_main, SY_FEXP_THREADS), SY_FEXP_THREADS, SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS), s>>>(
+        f, raw_in, w.n_main, gt_out);
     LAUNCHED(ctx);
   }
   if (w.n_tail) {
     const size_t o = w.n_main;
-    k_final_exp<<<w.tail_blocks, w.tail_threads, 0, s>>>(f + o * 384, raw_in, w.n_tail, gt_out + o * 384);
+    k_final_exp<<<w.tail_blocks, w.tail_threads, SY_FEXP_SMEM_BYTES(w.tail_threads), s>>>(f + o * 384, raw_in, w.n_tail,
+                                                                                         gt_out + o * 384);
     LAUNCHED(ctx);
   }
   return 0;
@@ -1181,6 +1188,13 @@ int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device_id);
+  // opt-in for more than 48 KB of dynamic shared memory (the Miller loop's accumulators); per device
+  if (e == cudaSuccess && SY_MILLER_SMEM)
+    e = cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS));
+  if (e == cudaSuccess && SY_FEXP_SMEM)
+    e = cudaFuncSetAttribute(k_final_exp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fail, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_fail, 0, sizeof(int));
   if (e != cudaSuccess) {
@@ -1525,7 +1539,7 @@ static int launch_glued(sylow_b200_ctx* ctx, const uint8_t* g1v, size_t sv, cons
                         const uint8_t* g2v_inf, const uint8_t* g1f, size_t sf, const uint8_t* g1f_inf,
                         const uint8_t* tables, size_t n, uint8_t* f_out, cudaStream_t s) {
   // the opt-in for > 48 KB of dynamic shared memory is per device: remember it per context
-  size_t smem = (size_t)NF * SY_TABLE_BYTES;
+  size_t smem = (size_t)NF * SY_TABLE_BYTES + SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS);
   unsigned bit = 1u << (NV * 4 + NF);
   if (!(ctx->glued_attr_mask & bit)) {
     CK(cudaFuncSetAttribute(k_glued<NV, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -67,19 +67,56 @@ SY_HD_ADD Fp2 fp2_sub_mul_xi(const Fp2& t, const Fp2& a) {
 // operand depend on the previous one's last limb.
 #if defined(__CUDA_ARCH__)
 #define SY_AFTER(x, y) asm volatile("" : "+r"(x) : "r"(y))
+// every limb of v waits for y: nothing of the next product can be hoisted above the previous one
+#define SY_AFTER8(v, y)                            \
+  do {                                             \
+    _Pragma("unroll") for (int i_ = 0; i_ < 8; i_++) SY_AFTER((v)[i_], y); \
+  } while (0)
 #else
 #define SY_AFTER(x, y) ((void)0)
+#define SY_AFTER8(v, y) ((void)0)
 #endif
-SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
+#ifndef SY_FENCE_ALL
+#define SY_FENCE_ALL 1
+#endif
+#ifndef SY_VEC_LOAD
+#define SY_VEC_LOAD 1
+#endif
+// An Fp2 operand arrives by reference (generic pointer into the caller's frame); ptxas loads it limb by limb unless
+// told that the 64 bytes are four aligned 128-bit words (Fp is alignas(16)).
+SY_HD Fp2 fp2_ldv(const Fp2& a) {
+#if defined(__CUDA_ARCH__) && SY_VEC_LOAD
+  const uint4* p = reinterpret_cast<const uint4*>(&a);
+  uint4 w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+  Fp2 r;
+  r.c0.l[0] = w0.x; r.c0.l[1] = w0.y; r.c0.l[2] = w0.z; r.c0.l[3] = w0.w;
+  r.c0.l[4] = w1.x; r.c0.l[5] = w1.y; r.c0.l[6] = w1.z; r.c0.l[7] = w1.w;
+  r.c1.l[0] = w2.x; r.c1.l[1] = w2.y; r.c1.l[2] = w2.z; r.c1.l[3] = w2.w;
+  r.c1.l[4] = w3.x; r.c1.l[5] = w3.y; r.c1.l[6] = w3.z; r.c1.l[7] = w3.w;
+  return r;
+#else
+  return a;
+#endif
+}
+SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a_, const Fp2& b_) {
+  const Fp2 a = fp2_ldv(a_), b = fp2_ldv(b_);
   uint32_t t0[16], t1[16], t2[16], sa[8], sb[8], a1[8];
   fp_mul_wide(t0, a.c0.l, b.c0.l);
 #pragma unroll
   for (int i = 0; i < 8; i++) a1[i] = a.c1.l[i];
+#if SY_FENCE_ALL
+  SY_AFTER8(a1, t0[15]);
+#else
   SY_AFTER(a1[0], t0[15]);
+#endif
   fp_mul_wide(t1, a1, b.c1.l);
   fp_add_nr(sa, a.c0.l, a1);
   fp_add_nr(sb, b.c0.l, b.c1.l);
+#if SY_FENCE_ALL
+  SY_AFTER8(sa, t1[15]);
+#else
   SY_AFTER(sa[0], t1[15]);
+#endif
   fp_mul_wide(t2, sa, sb);
   wide_sub(t2, t0);
   wide_sub(t2, t1);
@@ -95,7 +132,8 @@ SY_HD_MUL2 Fp2 fp2_mul(const Fp2& a, const Fp2& b) {
 // fp2.rs:164-171: ((a0+a1)(a0-a1), 2 a0 a1).  The factors a0+a1 and a0-a1+p are left unreduced
 // (< 2p each, product < 4p^2 < p*R, which is all fp_mul needs) and 2 a0 a1 is doubled before its single
 // reduction (2 a0 a1 < 2p^2 < p*R).
-SY_HD_MUL2 Fp2 fp2_sqr(const Fp2& a) {
+SY_HD_MUL2 Fp2 fp2_sqr(const Fp2& a_) {
+  const Fp2 a = fp2_ldv(a_);
   Fp s, d, pp;
 #pragma unroll
   for (int i = 0; i < 8; i++) pp.l[i] = SY_TAB(kP)[i];
@@ -112,7 +150,11 @@ SY_HD_MUL2 Fp2 fp2_sqr(const Fp2& a) {
 }
 
 // FieldExtension::scale by a base-field element (extensions.rs:86-94)
-SY_HD_NOINLINE Fp2 fp2_mul_fp(const Fp2& a, const Fp& k) { return Fp2{fp_mul(a.c0, k), fp_mul(a.c1, k)}; }
+SY_HD_NOINLINE Fp2 fp2_mul_fp(const Fp2& a_, const Fp& k_) {
+  const Fp2 a = fp2_ldv(a_);
+  const Fp k = k_;
+  return Fp2{fp_mul(a.c0, k), fp_mul(a.c1, k)};
+}
 
 // fp2.rs:343-361
 SY_HD_NOINLINE Fp2 fp2_inv(const Fp2& a) {

@@ -72,8 +72,8 @@ int main(int argc, char** argv) {
   float ms_m = 0, ms_f = 0;
   unsigned gm = (unsigned)((n + SY_MILLER_THREADS - 1) / SY_MILLER_THREADS);
   unsigned gf = (unsigned)((n + SY_FEXP_THREADS - 1) / SY_FEXP_THREADS);
-  const size_t sm_m = SY_MILLER_SMEM ? (size_t)SY_MILLER_THREADS * SY_ACC_STRIDE : 0;
-  const size_t sm_f = SY_FEXP_SMEM ? (size_t)SY_FEXP_THREADS * SY_ACC_STRIDE : 0;
+  const size_t sm_m = SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS);
+  const size_t sm_f = SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS);
   CHECK(cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_m));
   CHECK(cudaFuncSetAttribute(k_final_exp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f));
   k_miller<<<gm, SY_MILLER_THREADS, sm_m>>>(g1, nullptr, g2, nullptr, 1, n, f, 1);

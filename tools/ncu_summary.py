@@ -34,6 +34,20 @@ def num(v):
         return None
 
 
+SCALE = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+
+
+def dram_bytes(d):
+    """read + write bytes of one launch; ncu picks a unit PER METRIC and per session (d carries them as <metric>@unit)"""
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        v = num(d.get(k, ""))
+        if v is None:
+            return None
+        tot += v * SCALE[d.get(k + "@unit", "byte")]
+    return tot
+
+
 def short(name):
     base = name.split("(")[0].replace("void ", "").replace("sylow_kernels::", "").strip()
     return base.split("<")[0]  # k_glued<1, 3> -> k_glued
@@ -83,8 +97,30 @@ def main():
     ki = hdr.index("Kernel Name")
     summary = {}
     launches = collections.defaultdict(list)
+    def with_units(h, u, r):
+        d = dict(zip(h, r))
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if k in h:
+                d[k + "@unit"] = u[h.index(k)]
+        return d
+
     for r in rows[2:]:
-        launches[short(r[ki])].append(dict(zip(hdr, r)))
+        launches[short(r[ki])].append(with_units(hdr, units, r))
+    # per-kernel sessions (tools/gpu_profile_one.sh): in a session with many kernels ncu sometimes collects only the
+    # source-level passes for a kernel (6 instead of 39 passes, hardware counters "-nan"); a launch with hardware
+    # counters from its own session replaces the incomplete one
+    for fn in sorted(os.listdir(G)):
+        if fn.startswith(tag + "_raw_") and fn.endswith(".csv"):
+            rr = list(csv.reader(open(os.path.join(G, fn))))
+            for r in rr[2:]:
+                d = with_units(rr[0], rr[1], r)
+                if num(d.get("smsp__inst_executed.sum", "")) is None:
+                    continue
+                k = short(d["Kernel Name"])
+                same = [x for x in launches[k] if x["launch__grid_size"] == d["launch__grid_size"]]
+                for x in same:
+                    launches[k].remove(x)
+                launches[k].append(d)
     md = []
     for kname, ls in launches.items():
         # the kernel's main launch (largest grid); a low-occupancy tail launch of the same kernel is listed beside it
@@ -105,9 +141,7 @@ def main():
                  "alu_pct": m["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed"],
                  "issue_active_pct": m["smsp__issue_active.avg.pct_of_peak_sustained_active"],
                  "inst_executed": m["smsp__inst_executed.sum"],
-                 "dram_bytes": None if m["dram__bytes_read.sum"] is None else
-                 (m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[
-                     units[hdr.index("dram__bytes_read.sum")]],
+                 "dram_bytes": dram_bytes(d),
                  "local_ld_hit_pct": m["l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct"],
                  "local_st_hit_pct": m["l1tex__t_sector_pipe_lsu_mem_local_op_st_hit_rate.pct"],
                  "stall_per_issue": dict(sorted(stalls.items(), key=lambda kv: -(kv[1] or 0))[:8]),
