@@ -320,7 +320,9 @@ int sylow_b200_hash_failed_dev(sylow_b200_ctx* ctx, void* stream, int* failed);
  * 6 inv(a) by the Fermat ladder, 7 raw output (a / p) + 1 from the Jacobi iteration, + 4 if a^((p-1)/2) disagrees. */
 int sylow_b200_fp_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 /* out[i] = a[i] (op) b[i] on Fp12; op: 0 mul, 1 sqr(a), 2 inv(a), 3/4/5 frobenius^{1,2,3}(a),
- * 6 cyclotomic_squared(a), 7 a.sparse_mul(b.c0.c0, b.c0.c1, b.c0.c2). */
+ * 6 cyclotomic_squared(a), 7 a.sparse_mul(b.c0.c0, b.c0.c1, b.c0.c2).  The lower tower levels on their own, operands in
+ * the leading coefficients (a2 = a.c0.c0, a6 = a.c0) and zeros elsewhere in the output: 8 Fp2 mul, 9 Fp2 sqr, 10 Fp6 mul,
+ * 11 Fp6 sqr, 12 Fp2 inv, 13 (xi a2, b2 + xi a2, b2 - xi a2), 14 Fp6 inv, 15 (a2 * b.c0.c0.c0, a2 / 2, conj(a2)). */
 int sylow_b200_fp12_op_batch(sylow_b200_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 /* out[i] = the batch-verification weight r_(first_index + i) derived from weight_seed (tests). */
 int sylow_b200_batch_weights(sylow_b200_ctx* ctx, const uint8_t* weight_seed /* 32 B */, uint64_t first_index, size_t n,

@@ -180,6 +180,32 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul_u64(const Proj<F>& p, uint64_t k) {
   return acc;
 }
 
+// Signed 4-bit windows of a magnitude of NW * 4 bits whose top window is at most 7: digits in [-8, 8], least significant
+// first.  A table of the multiples 0..8 then serves every window (half the table of unsigned windows, half the
+// additions to build it); a negative digit negates the selected point's y.
+template <int NW>
+SY_HD void signed_windows4(const uint32_t* mag, int8_t* digit) {
+  int carry = 0;
+  for (int w = 0; w < NW; w++) {
+    int d = (int)((mag[w >> 3] >> ((w & 7) * 4)) & 15u) + carry;
+    carry = d > 8;
+    digit[w] = (int8_t)(d - (carry << 4));
+  }
+}
+// multiples 0..8 of p
+template <class F>
+SY_HD void small_multiples(Proj<F>* tab, const Proj<F>& p) {
+  tab[0] = proj_zero<F>();
+  tab[1] = p;
+  tab[2] = proj_double(p);
+  tab[3] = proj_add(tab[2], p);
+  tab[4] = proj_double(tab[2]);
+  tab[5] = proj_add(tab[4], p);
+  tab[6] = proj_double(tab[3]);
+  tab[7] = proj_add(tab[6], p);
+  tab[8] = proj_double(tab[4]);
+}
+
 // ---- GLV scalar multiplication --------------------------------------------------------------------
 // phi(x, y) = (beta x, y) is an endomorphism of both curves (j = 0) and acts on the r-torsion as
 // multiplication by lambda, lambda^2 + lambda + 1 = 0 mod r.  k = k1 + k2 lambda (mod r) with
@@ -250,10 +276,11 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul_glv(const Proj<F>& p, const uint32_t* k) 
   uint32_t k1[4], k2[4];
   bool neg1, neg2;
   glv_decompose(k, k1, neg1, k2, neg2);
-  Proj<F> tab[16];
-  tab[0] = proj_zero<F>();
-  tab[1] = p;
-  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
+  int8_t d1[32], d2[32];
+  signed_windows4<32>(k1, d1);  // |k1|, |k2| < 2^127: the top window is at most 7
+  signed_windows4<32>(k2, d2);
+  Proj<F> tab[9];
+  small_multiples(tab, p);
   Proj<F> acc = proj_zero<F>();
   for (int w = 31; w >= 0; w--) {
     SY_LOOP_SYNC();
@@ -263,12 +290,13 @@ SY_HD_NOINLINE Proj<F> proj_scalar_mul_glv(const Proj<F>& p, const uint32_t* k) 
       acc = proj_double(acc);
       acc = proj_double(acc);
     }
-    Proj<F> t = tab[(k1[w >> 3] >> ((w & 7) * 4)) & 15u];
-    if (neg1) t.y = f_neg(t.y);
+    int a = d1[w], b = d2[w];
+    Proj<F> t = tab[a < 0 ? -a : a];
+    if (neg1 != (a < 0)) t.y = f_neg(t.y);
     acc = proj_add(acc, t);
-    t = tab[(k2[w >> 3] >> ((w & 7) * 4)) & 15u];
+    t = tab[b < 0 ? -b : b];
     t.x = f_mul_beta(t.x);
-    if (neg2) t.y = f_neg(t.y);
+    if (neg2 != (b < 0)) t.y = f_neg(t.y);
     acc = proj_add(acc, t);
   }
   return acc;
@@ -340,10 +368,10 @@ SY_HD_NOINLINE G2Proj g2_scalar_mul_gls(const G2Proj& p, const uint32_t* k) {
   uint32_t mag[4][3];
   bool neg[4];
   gls_decompose(k, mag, neg);
-  G2Proj tab[16];
-  tab[0] = proj_zero<Fp2>();
-  tab[1] = p;
-  for (int i = 2; i < 16; i++) tab[i] = (i & 1) ? proj_add(tab[i - 1], p) : proj_double(tab[i >> 1]);
+  int8_t dg[4][17];
+  for (int e = 0; e < 4; e++) signed_windows4<17>(mag[e], dg[e]);  // |k_j| < 2^67: the top window is at most 7
+  G2Proj tab[9];
+  small_multiples(tab, p);
   G2Proj acc = proj_zero<Fp2>();
   for (int w = 16; w >= 0; w--) {
     SY_LOOP_SYNC();
@@ -354,8 +382,9 @@ SY_HD_NOINLINE G2Proj g2_scalar_mul_gls(const G2Proj& p, const uint32_t* k) {
       acc = proj_double(acc);
     }
     for (int e = 0; e < 4; e++) {
-      G2Proj t = g2_psi_pow(tab[(mag[e][w >> 3] >> ((w & 7) * 4)) & 15u], e);
-      if (neg[e]) t.y = fp2_neg(t.y);
+      int d = dg[e][w];
+      G2Proj t = g2_psi_pow(tab[d < 0 ? -d : d], e);
+      if (neg[e] != (d < 0)) t.y = fp2_neg(t.y);
       acc = proj_add(acc, t);
     }
   }

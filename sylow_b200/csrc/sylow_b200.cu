@@ -47,6 +47,9 @@ using namespace sylow;
 #endif
 #define SY_SMALL_THREADS 128
 
+#ifndef SY_VERIFY_GLUE
+#define SY_VERIFY_GLUE 0  // signatures per thread in verify_batch's Miller stage: 0 = by batch size, or 1, 2, 4; SYLOW_B200_VERIFY_GLUE overrides
+#endif
 struct DstPrime {
   uint8_t b[256];
   uint32_t len;
@@ -833,7 +836,17 @@ k_fp12_op(int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     case 4: r = fp12_frobenius(x, 2); break;
     case 5: r = fp12_frobenius(x, 3); break;
     case 6: r = cyclotomic_squared(x); break;
-    default: r = fp12_sparse_mul(x, y.c0.c0, y.c0.c1, y.c0.c2);
+    case 7: r = fp12_sparse_mul(x, y.c0.c0, y.c0.c1, y.c0.c2); break;
+    // the tower's lower levels on their own (operands in the leading coefficients, the rest of the output is 0)
+    case 8: r = Fp12{Fp6{fp2_mul(x.c0.c0, y.c0.c0), fp2_zero(), fp2_zero()}, fp6_zero()}; break;
+    case 9: r = Fp12{Fp6{fp2_sqr(x.c0.c0), fp2_zero(), fp2_zero()}, fp6_zero()}; break;
+    case 10: r = Fp12{fp6_mul(x.c0, y.c0), fp6_zero()}; break;
+    case 11: r = Fp12{fp6_sqr(x.c0), fp6_zero()}; break;
+    case 12: r = Fp12{Fp6{fp2_inv(x.c0.c0), fp2_zero(), fp2_zero()}, fp6_zero()}; break;
+    case 13: r = Fp12{Fp6{fp2_mul_xi(x.c0.c0), fp2_mul_xi_add(x.c0.c0, y.c0.c0), fp2_sub_mul_xi(y.c0.c0, x.c0.c0)}, fp6_zero()}; break;
+    case 14: r = Fp12{fp6_inv(x.c0), fp6_zero()}; break;
+    case 15: r = Fp12{Fp6{fp2_mul_fp(x.c0.c0, y.c0.c0.c0), fp2_halve(x.c0.c0), fp2_conj(x.c0.c0)}, fp6_zero()}; break;
+    default: r = fp12_one();
   }
   if (i0 >= n) return;
   fp12_store(out + i * 384, r);
@@ -1172,6 +1185,12 @@ static int launch_final_exp(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, s
   return 0;
 }
 
+// defined further down (needs the table constants): one glued loop of NV fused + NF table pairs per item
+template <int NV, int NF>
+static int launch_glued(sylow_b200_ctx* ctx, const uint8_t* g1v, size_t sv, const uint8_t* g1v_inf, const uint8_t* g2v,
+                        const uint8_t* g2v_inf, const uint8_t* g1f, size_t sf, const uint8_t* g1f_inf,
+                        const uint8_t* tables, size_t n, uint8_t* f_out, cudaStream_t s);
+
 extern "C" {
 
 int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
@@ -1410,11 +1429,23 @@ int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, c
   size_t n = k * n_checks;
   if (n && (!g1 || !g2)) return SYLOW_B200_ERR_ARG;
   cudaStream_t s = pick(ctx, stream);
+  size_t k_prod = k;  // Miller values per check left for k_check_products to multiply
   if (n) {
     CKS(reserve(ctx, ctx->scratch0, n * 384));
-    CKS(launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, ctx->scratch0.p, 1, s));
+    // 2- and 4-pair checks (ecPairing, Groth16 without fixed tables) as ONE glued loop per check: one Fp12 squaring per
+    // digit for all pairs of the check, like glued_miller_loop (pairing.rs:970-1022); needs enough checks to fill the GPU
+    const size_t wave = (size_t)ctx->sms * SY_MILLER_THREADS * SY_MILLER_MINB;
+    if (k == 2 && n_checks >= wave) {
+      CKS((launch_glued<2, 0>(ctx, g1, 2, g1_inf, g2, g2_inf, nullptr, 0, nullptr, nullptr, n_checks, ctx->scratch0.p, s)));
+      k_prod = 1;
+    } else if (k == 4 && n_checks >= wave / 2) {
+      CKS((launch_glued<4, 0>(ctx, g1, 4, g1_inf, g2, g2_inf, nullptr, 0, nullptr, nullptr, n_checks, ctx->scratch0.p, s)));
+      k_prod = 1;
+    } else {
+      CKS(launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, ctx->scratch0.p, 1, s));
+    }
   }
-  k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, k, n_checks, ok_out);
+  k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, k_prod, n_checks, ok_out);
   LAUNCHED(ctx);
   return 0;
 }
@@ -1664,7 +1695,45 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
     LAUNCHED(ctx);
     CKS(g1_batch_affine(ctx, ctx->proj.p, n, 0, d_hm, d_hm_inf, s));
   }
-  CKS(launch_miller(ctx, d_hm, d_hm_inf, d_pks, d_pks_inf, n, ctx->scratch0.p, 1, s));
+  // The n Miller loops (-r_i H(m_i), pk_i) only ever meet as a product, so SY_VERIFY_GLUE signatures share one thread
+  // and ONE Fp12 squaring per loop digit - what glued_miller_loop does for the whole batch in the reference
+  // (pairing.rs:970-1022).  A thread's 2 / 4 pairs save 63 x 36 of the 8 444 multiplications of every pair after its
+  // first.  The n % GLUE leftover pairs go through k_miller.
+  static const int glue_env = [] {
+    const char* v = getenv("SYLOW_B200_VERIFY_GLUE");
+    int g = v ? atoi(v) : SY_VERIFY_GLUE;
+    return g == 1 || g == 2 || g == 4 ? g : 0;
+  }();
+  int glue = glue_env;
+  if (!glue) {
+    // fewest wave-times: whole waves of n / g threads (256 resident per SM) times the multiplications of g glued pairs.
+    // Measured at 2^20 signatures (profiles/r02_verify_glue.jsonl): 192.4 / 171.2 / 163.3 ms for 1 / 2 / 4; at 2^13 the
+    // order reverses (9.3 / 12.4 / 18.4 ms: a quarter of the threads, each four times as long).
+    const size_t wave = (size_t)ctx->sms * SY_MILLER_THREADS * SY_MILLER_MINB;
+    const size_t cost[3] = {8444, 2 * 8444 - 2268, 4 * 8444 - 3 * 2268};
+    size_t best = ~(size_t)0;
+    for (int j = 0; j < 3; j++) {
+      const size_t g = (size_t)1 << j, waves = (n / g + wave - 1) / wave;
+      if (n >= g && waves * cost[j] < best) {
+        best = waves * cost[j];
+        glue = (int)g;
+      }
+    }
+  }
+  size_t n_f = n;  // Miller values in scratch0 before the signature pair's value is appended
+  if (glue > 1 && n >= (size_t)glue) {
+    const size_t items = n / glue, done = items * glue;
+    if (glue == 2)
+      CKS((launch_glued<2, 0>(ctx, d_hm, 2, d_hm_inf, d_pks, d_pks_inf, nullptr, 0, nullptr, nullptr, items, ctx->scratch0.p, s)));
+    else
+      CKS((launch_glued<4, 0>(ctx, d_hm, 4, d_hm_inf, d_pks, d_pks_inf, nullptr, 0, nullptr, nullptr, items, ctx->scratch0.p, s)));
+    if (done < n)
+      CKS(launch_miller(ctx, d_hm + done * 64, d_hm_inf + done, d_pks + done * 128, d_pks_inf ? d_pks_inf + done : nullptr,
+                        n - done, ctx->scratch0.p + items * 384, 1, s));
+    n_f = items + (n - done);
+  } else {
+    CKS(launch_miller(ctx, d_hm, d_hm_inf, d_pks, d_pks_inf, n, ctx->scratch0.p, 1, s));
+  }
   if (weighted) {
     k_g1_mul_weight<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_sigs, d_sigs_inf, ws, first_index, n,
                                                                        ctx->proj.p);
@@ -1674,8 +1743,8 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
     CKS(g1_sum_reduce(ctx, d_sigs, d_sigs_inf, n, 0, d_sum, d_sum_inf, s));
   }
   CKS((launch_glued<0, 1>(ctx, nullptr, 0, nullptr, nullptr, nullptr, d_sum, 1, d_sum_inf, ctx->d_gen_table, 1,
-                          ctx->scratch0.p + n * 384, s)));
-  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n + 1, d_f_out, 0, s);
+                          ctx->scratch0.p + n_f * 384, s)));
+  return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n_f + 1, d_f_out, 0, s);
 }
 
 // *failed = 1 if a hash-to-curve of the last hashing `_dev` call enqueued on `stream` hit SvdW's failing square-root

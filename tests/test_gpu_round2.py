@@ -267,3 +267,86 @@ def test_hash_failed_dev_flag(eng):
     assert eng.hash_failed_dev() is False
     exp = [o.proj_to_affine(o.FpOps, o.hash_to_curve_g1(m)) for m in MSGS]
     assert [w.b_g1(bytes(r)) for r in d_out.cpu().numpy()] == exp
+
+
+# ------------------------------------------------------------------------------------------ Fp2 / Fp6 on their own
+def test_fp2_fp6_direct_ops(eng):
+    """the lower tower levels directly on the GPU (fp12_op 8-15), not only through Fp12
+    operations - edge coefficients (0, 1, p - 1, the value whose Montgomery form is p - 1) and random ones, against
+    the oracle (src/fields/fp2.rs:99-171,269-361; fp6.rs:189-236,267-424)."""
+    rng = random.Random(205)
+    P = o.P
+    top = (P - 1) * pow(1 << 256, -1, P) % P  # Montgomery representative p - 1: the largest limbs the kernels see
+    edge = [0, 1, 2, P - 1, P - 2, top, (P + 1) // 2, (P - 1) // 2]
+    cases = [([rng.choice(edge) for _ in range(12)], [rng.choice(edge) for _ in range(12)]) for _ in range(200)]
+    cases += [([rng.randrange(P) for _ in range(12)], [rng.randrange(P) for _ in range(12)]) for _ in range(300)]
+    cases += [([v] * 12, [w_] * 12) for v in edge for w_ in edge]
+    A = arr([w.fp12_b(o.fp12_from_list(a)) for a, _ in cases])
+    B = arr([w.fp12_b(o.fp12_from_list(b)) for _, b in cases])
+    got = {op: [o.fp12_to_list(w.b_fp12(bytes(r))) for r in eng.fp12_op_batch(op, A, B)] for op in range(8, 16)}
+    inv2 = o.TWO_INV
+    for i, (a, b) in enumerate(cases):
+        a2, b2 = (a[0], a[1]), (b[0], b[1])
+        a6 = ((a[0], a[1]), (a[2], a[3]), (a[4], a[5]))
+        b6 = ((b[0], b[1]), (b[2], b[3]), (b[4], b[5]))
+        flat2 = lambda x: [x[0], x[1]]
+        flat6 = lambda x: [c for t in x for c in t]
+        assert got[8][i][:2] == flat2(o.fp2_mul(a2, b2)) and not any(got[8][i][2:])
+        assert got[9][i][:2] == flat2(o.fp2_sqr(a2)) and not any(got[9][i][2:])
+        assert got[10][i][:6] == flat6(o.fp6_mul(a6, b6)) and not any(got[10][i][6:])
+        assert got[11][i][:6] == flat6(o.fp6_sqr(a6))
+        assert got[12][i][:2] == flat2(o.fp2_inv(a2))
+        xi = o.fp2_residue_mul(a2)
+        assert got[13][i][:6] == flat2(xi) + flat2(o.fp2_add(b2, xi)) + flat2(o.fp2_sub(b2, xi))
+        assert got[14][i][:6] == flat6(o.fp6_inv(a6))
+        assert got[15][i][:6] == [a[0] * b[0] % P, a[1] * b[0] % P, a[0] * inv2 % P, a[1] * inv2 % P, a[0], -a[1] % P]
+
+
+# ------------------------------------------------------------------------------------------ glued loops for 2-/4-pair checks
+def test_glued_pairing_checks_large(eng):
+    """pairing_check_batch with 2 and 4 pairs per check runs ONE glued loop per check once there are enough checks to fill
+    the GPU (one Fp12 squaring per digit for all pairs of a check, pairing.rs:970-1022); below that it multiplies separate
+    Miller values.  Both forms must give the same verdicts: e(a P, Q) e(-a P, Q) = 1 and e(aP,Q) e(bP,Q) e(cP,Q) e(-(a+b+c)P, Q)
+    = 1, with broken checks and infinite pairs sprinkled in."""
+    import torch
+
+    rng = random.Random(206)
+    nchk = 148 * 256 + 333  # more than one wave of checks
+    dev = torch.device("cuda", 0)
+
+    def scalars(vals):
+        return torch.from_numpy(arr([w.fp_b(v % o.R_ORDER) for v in vals])).to(dev)
+
+    for k in (2, 4):
+        n = nchk * k
+        base = [rng.randrange(1, o.R_ORDER) for _ in range(64)]
+        a = [base[(i * 7 + j) % 64] + i * 1000003 + j for i in range(nchk) for j in range(k - 1)]
+        ks = []
+        for i in range(nchk):
+            row = a[i * (k - 1):(i + 1) * (k - 1)]
+            ks += row + [-sum(row)]
+        bad = sorted(rng.sample(range(nchk), 40))
+        for c in bad:
+            ks[c * k] += 1
+        d_g1 = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+        d_g2 = torch.empty((n, 128), dtype=torch.uint8, device=dev)
+        g1gen = torch.from_numpy(np.tile(np.frombuffer(w.g1_b(o.G1_GEN), np.uint8), (n, 1))).to(dev)
+        g2gen = torch.from_numpy(np.tile(np.frombuffer(w.g2_b(o.G2_GEN), np.uint8), (n, 1))).to(dev)
+        eng.g1_mul_batch_dev(g1gen, scalars(ks), d_g1)
+        q = rng.randrange(1, o.R_ORDER)
+        eng.g2_mul_batch_dev(g2gen, scalars([q] * n), d_g2)
+        inf1 = np.zeros(n, np.uint8)
+        skip = [c for c in rng.sample(range(nchk), 30) if c not in bad]
+        for c in skip:  # an infinite pair contributes 1: the rest of the check no longer cancels
+            inf1[c * k + 1] = 1
+        expect = np.ones(nchk, bool)
+        expect[bad] = False
+        expect[skip] = False
+        d_ok = torch.empty(nchk, dtype=torch.uint8, device=dev)
+        eng.pairing_check_batch_dev(d_g1, d_g2, k, d_ok, d_g1_inf=torch.from_numpy(inf1).to(dev))
+        got = d_ok.cpu().numpy().astype(bool)
+        assert (got == expect).all(), (k, int((got != expect).sum()))
+        # the small-batch path (separate Miller values) on a prefix agrees
+        m = 64
+        small = eng.pairing_check_batch(d_g1[: m * k].cpu().numpy(), d_g2[: m * k].cpu().numpy(), k, g1_inf=inf1[: m * k])
+        assert (small == expect[:m]).all()
