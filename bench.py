@@ -499,9 +499,9 @@ def main():
         ms_v_kernels = time_ms(lambda: eng.verify_batch_partial_dev(d_pk, d_msgs, d_offs, d_sigs, d_part), reps=3)
         d_hm = torch.empty((nv, 64), dtype=torch.uint8, device=dev)
         ms_hash = time_ms(lambda: eng.hash_to_g1_batch_dev(d_msgs, d_offs, d_hm), reps=3)
-        d_fv = torch.empty((nv, 384), dtype=torch.uint8, device=dev)
-        ms_vm = time_ms(lambda: eng.miller_loop_batch_dev(d_hm, d_pk, d_fv), reps=3)
-        del d_fv
+        # the Miller stage (k_glued<4,0>, which has no entry point of its own, plus the signature sum and the product
+        # tree, about 3 %) = the partial product minus the hash, both event-timed on the same buffers
+        ms_vm = max(ms_v_kernels - ms_hash, 1e-3)
         # negative case inside the job: the LAST signature of the LAST rank is replaced; every rank must say False
         bad = sigs.copy()
         if rank == world - 1:
@@ -530,17 +530,24 @@ def main():
             ok1 = eng.verify_batch_same_signer(pk1[0], packed, sigs1)
             same_signer = {"verifies_per_s": nv / (time.perf_counter() - t1), "batch_ok": bool(ok1),
                            "note": "one signer: n hashes + 2n point additions + two Miller loops per batch, host buffers (e2e)"}
-        v_roof = roofline_block("k_miller", "verify_batch_partial (k_hash_to_g1 + k_g1_batch_affine + k_miller + sums)", nv,
+        v_roof = roofline_block("verify", "verify_batch_partial (k_hash_to_g1 + k_g1_batch_affine + k_glued<4,0> + sums)", nv,
                                 FP_MUL_HASH_TO_G1 + FP_MUL_MILLER_FUSED, ms_v_kernels, peak, analytic, None, 128 + 32 + 64,
-                                "per signature: hash-to-curve 2 900 + fused Miller loop 8 444 Fp multiplications; the "
-                                "signature side is one point addition per signature and ONE Miller loop per batch")
+                                "per signature: hash-to-curve 2 900 + fused Miller loop 8 444 Fp multiplications (SURVEY's "
+                                "units).  The kernels execute fewer: four signatures share a thread and ONE Fp12 squaring per "
+                                "loop digit (63 x 36 multiplications saved for 3 of every 4 pairs), the hash runs binary-GCD / "
+                                "Jacobi iterations instead of 5 of its 7 ladders, and the signature side is one point "
+                                "addition per signature plus ONE Miller loop per batch - so this fraction can exceed 1; "
+                                "the per-kernel blocks carry the executed rates")
         v_roof["kernels"] = {
             "k_hash_to_g1": roofline_block("k_hash_to_g1", "k_hash_to_g1 (+ k_g1_batch_affine)", nv, FP_MUL_HASH_TO_G1, ms_hash,
                                            peak, analytic, ncu, 32 + 64,
                                            "SURVEY's unit counts 7 Fermat ladders; 5 of them are binary-GCD / Jacobi "
                                            "iterations here (ALU work, no multiplier), so the executed rate is far lower"),
-            "k_miller": roofline_block("k_miller", "k_miller on (-H(m_i), pk_i)", nv, FP_MUL_MILLER_FUSED, ms_vm, peak, analytic,
-                                       ncu, 192 + 384)}
+            "k_glued<4,0>": roofline_block("k_glued<4,0>", "k_glued<4,0>: four (-H(m_i), pk_i) pairs per thread, shared squarings (+ signature sum, product tree)",
+                                           nv, FP_MUL_MILLER_FUSED, ms_vm, peak, analytic,
+                                           {"k_glued<4,0>": dict(ncu.get("k_glued<4,0>") or {}, n=4 * (ncu.get("k_glued<4,0>") or {}).get("n", 0))}
+                                           if ncu.get("k_glued<4,0>") else None, 192 + 96,
+                                           "unit = one separate fused Miller loop per pair (8 444); executed: 8 444 - 3/4 x 2 268")}
         verify = {"metric": "bls_verifies_per_s", "value": world * nv / dt_v, "unit": "verifies/s",
                   "signatures_per_gpu": nv, "distinct_signers": nv, "batch_ok": bool(ok and ok_e),
                   "ms_per_batch": dt_v * 1e3, "reps": 5,
@@ -576,7 +583,7 @@ def main():
         extras["groth16_4pair_checks_per_s"] = world * nc / (max_over_ranks(ms_g) * 1e-3)
         extras["groth16_checks_per_gpu"] = nc
         extras["groth16_roofline"] = roofline_block(
-            "k_glued", "k_glued<1,3> + k_check_products (4-pair glued loop, one final exponentiation per check)", nc,
+            "k_glued<1,3>", "k_glued<1,3> + k_check_products (4-pair glued loop, one final exponentiation per check)", nc,
             FP_MUL_GROTH16_CHECK, ms_g, peak, analytic, ncu, 4 * 64 + 128 + 1,
             "per check: fused pair 8 444 + 3 table pairs x (6 045 - 63 shared squarings x 36) + final exponentiation 9 202")
         # config #5: variable-base scalar multiplication, 254-bit scalars

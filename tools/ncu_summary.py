@@ -49,8 +49,8 @@ def dram_bytes(d):
 
 
 def short(name):
-    base = name.split("(")[0].replace("void ", "").replace("sylow_kernels::", "").strip()
-    return base.split("<")[0]  # k_glued<1, 3> -> k_glued
+    base = name.replace("(int)", "").split("(")[0].replace("void ", "").replace("sylow_kernels::", "").strip()
+    return base.replace(" ", "")  # "void k_glued<(int)1, (int)3>(...)" -> "k_glued<1,3>"
 
 
 def opcode_table(path):
@@ -92,11 +92,12 @@ def opcode_table(path):
 
 
 def main():
-    rows = list(csv.reader(open(os.path.join(G, "%s_prof_raw.csv" % tag))))
-    hdr, units = rows[0], rows[1]
-    ki = hdr.index("Kernel Name")
     summary = {}
     launches = collections.defaultdict(list)
+    main = os.path.join(G, "%s_prof_raw.csv" % tag)
+    rows = list(csv.reader(open(main))) if os.path.exists(main) else [[], []]
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name") if hdr else 0
     def with_units(h, u, r):
         d = dict(zip(h, r))
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -128,12 +129,12 @@ def main():
         d = ls[0]
         items = n_items
         threads = (num(d["launch__grid_size"]) or 0) * (num(d["launch__block_size"]) or 0)
-        if kname.startswith("k_glued") or kname == "k_check_products":
+        if kname.startswith("k_glued<1,3>") or kname.startswith("k_glued<4,0>") or kname == "k_check_products":
             items = n_items // 4
-        elif len(ls) > 1:
-            items = int(threads) if threads < n_items else n_items
+        elif 0 < threads < n_items:
+            items = int(threads)  # the kernel's main launch covers the whole waves only (a tail launch does the rest)
         m = {k: num(d.get(k, "")) for k in KEYS}
-        stalls = {h.split("issue_stalled_")[1].split("_per_issue")[0]: num(d[h]) for h in hdr
+        stalls = {h.split("issue_stalled_")[1].split("_per_issue")[0]: num(d[h]) for h in d
                   if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and num(d[h]) is not None}
         entry = {"n": items, "ms": m["gpu__time_duration.sum"], "grid": m["launch__grid_size"], "block": m["launch__block_size"],
                  "registers": m["launch__registers_per_thread"],

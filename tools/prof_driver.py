@@ -40,5 +40,9 @@ for _round in range(2):  # ncu skips the first round (-s 8): cold first launches
     eng.tables_to_device(co, d_tab)
     d_ok = torch.empty(nc, dtype=torch.uint8, device=dev)
     eng.pairing_check_fixed_batch_dev(d_g1, d_g2[:nc].contiguous(), d_tab, 1, 3, d_ok)  # k_glued<1,3>, k_check_products
+    # verify_batch's Miller stage: k_hash_to_g1 again, then k_glued<4,0> (four signatures per thread) on (-H(m_i), pk_i);
+    # the signatures here are not valid ones - the kernels are branch-free in the data
+    d_part = torch.empty(384, dtype=torch.uint8, device=dev)
+    eng.verify_batch_partial_dev(d_g2, d_msgs, d_offs, d_g1, d_part)
     torch.cuda.synchronize()
 print("prof_driver done", n)
