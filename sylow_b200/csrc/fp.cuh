@@ -962,6 +962,37 @@ SY_HD_NOINLINE int fp_jacobi(const Fp& v) {
   return rest ? 0 : ((t & 1u) ? -1 : 1);
 }
 
+// Two Jacobi symbols in one loop: the 510 steps are a serial dependency chain (subtract, select, shift, repeat), so two
+// independent inputs interleaved in the same iterations give the scheduler twice the work per stall.  SvdW tests g(x1)
+// and g(x2) for squareness (svdw.rs:211-222), which do not depend on each other.
+SY_HD_NOINLINE void fp_jacobi2(const Fp& v0, const Fp& v1, int& j0, int& j1) {
+  uint32_t a[8], n[8], b[8], m[8], t = 0, u = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = v0.l[i];
+    b[i] = v1.l[i];
+    n[i] = m[i] = SY_TAB(kP)[i];
+  }
+#pragma unroll 1
+  for (int it = 0; it < SY_GCD_STEPS; it++) {
+    uint32_t a0 = a[0], n0 = n[0], b0 = b[0], m0 = m[0], odd, sw, odd2, sw2;
+    bingcd_step(a, n, odd, sw);
+    bingcd_step(b, m, odd2, sw2);
+    t ^= ((a0 & n0) >> 1) & sw;
+    t ^= (n[0] >> 1) ^ (n[0] >> 2);
+    u ^= ((b0 & m0) >> 1) & sw2;
+    u ^= (m[0] >> 1) ^ (m[0] >> 2);
+  }
+  uint32_t rest = n[0] ^ 1u, rest2 = m[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    rest |= n[i];
+    rest2 |= m[i];
+  }
+  j0 = rest ? 0 : ((t & 1u) ? -1 : 1);
+  j1 = rest2 ? 0 : ((u & 1u) ? -1 : 1);
+}
+
 // (f u + g v) / 2^32 mod p for u, v < p and signed f, g with |f| + |g| <= 2^30: negative factors act on p - u, the sum
 // (< 2^30 p) takes one Montgomery step (< 1.25 p) and one conditional subtraction.
 SY_HD void bingcd_lincomb(uint32_t* r, int32_t f, const uint32_t* u, int32_t g, const uint32_t* v) {

@@ -301,9 +301,11 @@ SY_HD void svdw_head(const Fp& u, Fp& tv1, Fp& tv2, Fp& d) {
 SY_HD_NOINLINE bool svdw_tail(const Fp& u, const Fp& tv1, const Fp& tv2, const Fp& tv3, Fp& x, Fp& y) {
   Fp tv4 = fp_mul(fp_mul(fp_mul(u, tv1), tv3), SY_TAB(kSvdwC3)[0]);
   Fp x1 = fp_sub(SY_TAB(kSvdwC2)[0], tv4);
-  bool e1 = fp_is_square(svdw_g(x1));
   Fp x2 = fp_add(SY_TAB(kSvdwC2)[0], tv4);
-  bool e2 = fp_is_square(svdw_g(x2)) & !e1;
+  int j1, j2;
+  fp_jacobi2(svdw_g(x1), svdw_g(x2), j1, j2);  // is_square (true for 0, fp.rs:625-631) of both candidates at once
+  bool e1 = j1 >= 0;
+  bool e2 = (j2 >= 0) & !e1;
   Fp x3 = fp_mul(fp_sqr(tv2), tv3);
   x3 = fp_add(fp_mul(fp_sqr(x3), SY_TAB(kSvdwC4)[0]), SY_TAB(kSvdwZ)[0]);
   x = fp_select(e1, x1, x3);

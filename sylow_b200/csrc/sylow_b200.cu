@@ -1660,12 +1660,12 @@ static bool load_seed(const uint8_t* weight_seed, WeightSeed& ws) {
   return true;
 }
 
-int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_pks_inf,
-                                        const uint8_t* d_msgs, const uint64_t* d_offsets, const uint8_t* d_sigs,
-                                        const uint8_t* d_sigs_inf, size_t n, const uint8_t* dst, size_t dst_len,
-                                        int hash_id, const uint8_t* weight_seed, uint64_t first_index, uint8_t* d_f_out,
-                                        void* stream) {
-  ENTER_DEV(ctx);
+// `pairs_ready` (may be null): an event after which the keys and signatures are in device memory - the host entry point
+// copies them on its copy stream while the hash-to-curve kernel, which only needs the messages, already runs
+static int verify_partial_core(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_pks_inf, const uint8_t* d_msgs,
+                               const uint64_t* d_offsets, const uint8_t* d_sigs, const uint8_t* d_sigs_inf, size_t n,
+                               const uint8_t* dst, size_t dst_len, int hash_id, const uint8_t* weight_seed,
+                               uint64_t first_index, uint8_t* d_f_out, void* stream, cudaEvent_t pairs_ready) {
   if (!ctx || !d_f_out || (n && (!d_pks || !d_offsets || !d_sigs))) return SYLOW_B200_ERR_ARG;
   DstPrime dp;
   CKS(make_dst_prime(ctx, dst, dst_len, hash_id, dp));
@@ -1689,6 +1689,7 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
   uint8_t* d_sum = d_hm + ((n * 65 + 63) / 64) * 64;  // 64 B point + flag
   uint8_t* d_sum_inf = d_sum + 64;
   CKS(hash_launch(ctx, d_msgs, d_offsets, n, dp, 1, d_hm, d_hm_inf, s));
+  if (pairs_ready) CK(cudaStreamWaitEvent(s, pairs_ready, 0));
   if (weighted) {
     CKS(reserve(ctx, ctx->proj, n * 96));
     k_g1_mul_weight<<<nblocks(n, SY_MUL_THREADS), SY_MUL_THREADS, 0, s>>>(d_hm, d_hm_inf, ws, first_index, n, ctx->proj.p);
@@ -1745,6 +1746,16 @@ int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pk
   CKS((launch_glued<0, 1>(ctx, nullptr, 0, nullptr, nullptr, nullptr, d_sum, 1, d_sum_inf, ctx->d_gen_table, 1,
                           ctx->scratch0.p + n_f * 384, s)));
   return product_reduce(ctx, ctx->scratch0.p, ctx->scratch1.p, n_f + 1, d_f_out, 0, s);
+}
+
+int sylow_b200_verify_batch_partial_dev(sylow_b200_ctx* ctx, const uint8_t* d_pks, const uint8_t* d_pks_inf,
+                                        const uint8_t* d_msgs, const uint64_t* d_offsets, const uint8_t* d_sigs,
+                                        const uint8_t* d_sigs_inf, size_t n, const uint8_t* dst, size_t dst_len,
+                                        int hash_id, const uint8_t* weight_seed, uint64_t first_index, uint8_t* d_f_out,
+                                        void* stream) {
+  ENTER_DEV(ctx);
+  return verify_partial_core(ctx, d_pks, d_pks_inf, d_msgs, d_offsets, d_sigs, d_sigs_inf, n, dst, dst_len, hash_id,
+                             weight_seed, first_index, d_f_out, stream, nullptr);
 }
 
 // *failed = 1 if a hash-to-curve of the last hashing `_dev` call enqueued on `stream` hit SvdW's failing square-root
@@ -2143,14 +2154,31 @@ int sylow_b200_verify_batch_partial(sylow_b200_ctx* ctx, const uint8_t* pks, con
   if (!pks || !sigs) return SYLOW_B200_ERR_ARG;
   const uint8_t *dm, *dpk, *dsg, *dpki, *dsgi;
   const uint64_t* dof;
+  // messages first, on the compute stream: the hash-to-curve kernel starts as soon as they are there, while the keys
+  // and signatures (six times the bytes) still travel on the copy stream
   CKS(msgs_to_dev(ctx, msgs, offsets, n, &dm, &dof));
-  CKS(to_dev(ctx, ctx->in_a, pks, n * 128, &dpk));
-  CKS(to_dev(ctx, ctx->in_b, sigs, n * 64, &dsg));
-  CKS(to_dev(ctx, ctx->flag_a, pks_inf, n, &dpki));
-  CKS(to_dev(ctx, ctx->flag_b, sigs_inf, n, &dsgi));
+  CKS(reserve(ctx, ctx->in_a, n * 128));
+  CKS(reserve(ctx, ctx->in_b, n * 64));
+  if (pks_inf) CKS(reserve(ctx, ctx->flag_a, n));
+  if (sigs_inf) CKS(reserve(ctx, ctx->flag_b, n));
   CKS(reserve(ctx, ctx->out, 384));
-  CKS(sylow_b200_verify_batch_partial_dev(ctx, dpk, dpki, dm, dof, dsg, dsgi, n, dst, dst_len, hash_id, weight_seed,
-                                          first_index, ctx->out.p, nullptr));
+  dpk = ctx->in_a.p;
+  dsg = ctx->in_b.p;
+  dpki = pks_inf ? ctx->flag_a.p : nullptr;
+  dsgi = sigs_inf ? ctx->flag_b.p : nullptr;
+  cudaError_t e = cudaMemcpyAsync(ctx->in_a.p, pks, n * 128, cudaMemcpyHostToDevice, ctx->copy_in);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->in_b.p, sigs, n * 64, cudaMemcpyHostToDevice, ctx->copy_in);
+  if (e == cudaSuccess && pks_inf) e = cudaMemcpyAsync(ctx->flag_a.p, pks_inf, n, cudaMemcpyHostToDevice, ctx->copy_in);
+  if (e == cudaSuccess && sigs_inf) e = cudaMemcpyAsync(ctx->flag_b.p, sigs_inf, n, cudaMemcpyHostToDevice, ctx->copy_in);
+  if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_fork, ctx->copy_in);
+  int st_core = e == cudaSuccess ? verify_partial_core(ctx, dpk, dpki, dm, dof, dsg, dsgi, n, dst, dst_len, hash_id,
+                                                       weight_seed, first_index, ctx->out.p, nullptr, ctx->ev_fork)
+                                 : fail_cuda(ctx, e);
+  if (st_core) {
+    cudaStreamSynchronize(ctx->copy_in);  // the caller's buffers must not be in flight when we return
+    cudaStreamSynchronize(ctx->stream);
+    return st_core;
+  }
   CK(cudaMemcpyAsync(f_out, ctx->out.p, 384, cudaMemcpyDeviceToHost, ctx->stream));
   return check_hash_fail(ctx);
 }
