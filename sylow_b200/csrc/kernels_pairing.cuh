@@ -3,6 +3,7 @@
 // exactly the same code.
 #pragma once
 #include "wire.cuh"
+#include "pairing_lanes.cuh"
 
 #ifndef SY_MILLER_THREADS
 #define SY_MILLER_THREADS 128
@@ -29,6 +30,20 @@
 #define SY_FEXP_SMEM 0
 #endif
 #define SY_ACC_STRIDE 400
+// Two lanes per Miller loop (pairing_lanes.cuh): one PairSlot (1 024 bytes) per lane pair, padded to 1 040 so that
+// consecutive slots start four banks apart (the eight lanes of a 128-bit access phase are four pairs).
+#ifndef SY_LANES_THREADS
+#define SY_LANES_THREADS 128
+#endif
+#ifndef SY_LANES_MINB
+#define SY_LANES_MINB 2
+#endif
+#define SY_SLOT_STRIDE 1040
+#define SY_LANES_SMEM_BYTES(threads) ((size_t)((threads) / 2) * SY_SLOT_STRIDE)
+// two lanes per final exponentiation: FexpHot (768 bytes) per lane pair, padded the same way; FexpCold in global scratch
+#define SY_FHOT_STRIDE 784
+#define SY_FLANES_SMEM_BYTES(threads) ((size_t)((threads) / 2) * SY_FHOT_STRIDE)
+#define SY_FLANES_SCRATCH_BYTES(pairs) ((size_t)(pairs) * sizeof(sylow::FexpCold))
 #define SY_MILLER_SMEM_BYTES(threads) (SY_MILLER_SMEM ? (size_t)(threads) * SY_ACC_STRIDE : (size_t)0)
 #define SY_FEXP_SMEM_BYTES(threads) (SY_FEXP_SMEM ? (size_t)(threads) * SY_ACC_STRIDE : (size_t)0)
 
@@ -60,6 +75,35 @@ k_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, con
     fp12_store(f_out + i * 384, f);
 }
 
+// The same values as k_miller with two lanes per pair: thread 2k + role of a block works on pair k of the block.
+__global__ void __launch_bounds__(SY_LANES_THREADS, SY_LANES_MINB)
+k_miller_lanes(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g1_inf, const uint8_t* __restrict__ g2,
+               const uint8_t* __restrict__ g2_inf, size_t n, uint8_t* __restrict__ f_out, int raw_out) {
+  const int role = threadIdx.x & 1;
+  const unsigned slot = threadIdx.x >> 1;
+  size_t i0 = (size_t)blockIdx.x * (blockDim.x >> 1) + slot;
+  size_t i = i0 < n ? i0 : n - 1;  // surplus lane pairs redo the last item (every thread runs the loop)
+  bool inf = (g1_inf && g1_inf[i]) || (g2_inf && g2_inf[i]);
+  const uint8_t* p = g1 + i * 64;
+  const uint8_t* q = g2 + i * 128;
+  PairSlot& s = *reinterpret_cast<PairSlot*>(reinterpret_cast<char*>(sy_acc_smem) + (size_t)slot * SY_SLOT_STRIDE);
+  lanes_miller_loop(s, role, fp_load(p), fp_load(p + 32), fp2_load(q), fp2_load(q + 64));
+  if (i0 >= n) return;
+  // lane 0 stores c0, lane 1 stores c1
+  Fp6 h = role ? s.f.c1 : s.f.c0;
+  if (inf) h = role ? fp6_zero() : fp6_one();
+  uint8_t* o = f_out + i * 384 + role * 192;
+  if (raw_out) {
+    fp2_store_raw(o, h.c0);
+    fp2_store_raw(o + 64, h.c1);
+    fp2_store_raw(o + 128, h.c2);
+  } else {
+    fp2_store(o, h.c0);
+    fp2_store(o + 64, h.c1);
+    fp2_store(o + 128, h.c2);
+  }
+}
+
 __global__ void __launch_bounds__(SY_FEXP_THREADS, SY_FEXP_MINB)
 k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,6 +112,34 @@ k_final_exp(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out) {
   final_exponentiation_assign(f, SY_FEXP_SMEM ? acc_slot() : nullptr);
   if (i0 >= n) return;
   fp12_store(gt_out + i * 384, f);
+}
+
+// The same values as k_final_exp with two lanes per item.  `scratch` holds one FexpCold per launched lane pair
+// (gridDim.x * blockDim.x / 2 of them).
+__global__ void __launch_bounds__(SY_LANES_THREADS, SY_LANES_MINB)
+k_final_exp_lanes(const uint8_t* f_in, int raw_in, size_t n, uint8_t* gt_out, uint8_t* scratch) {
+  const int role = threadIdx.x & 1;
+  const unsigned slot = threadIdx.x >> 1;
+  size_t i0 = (size_t)blockIdx.x * (blockDim.x >> 1) + slot;
+  size_t i = i0 < n ? i0 : n - 1;
+  FexpHot& h = *reinterpret_cast<FexpHot*>(reinterpret_cast<char*>(sy_acc_smem) + (size_t)slot * SY_FHOT_STRIDE);
+  FexpCold& c = reinterpret_cast<FexpCold*>(scratch)[i0];
+  const uint8_t* p = f_in + i * 384 + role * 192;
+  Fp6 v;
+  if (raw_in)
+    v = Fp6{fp2_load_raw(p), fp2_load_raw(p + 64), fp2_load_raw(p + 128)};
+  else
+    v = Fp6{fp2_load(p), fp2_load(p + 64), fp2_load(p + 128)};
+  if (role) c.f.c1 = v;
+  else c.f.c0 = v;
+  SY_LANE_SYNC();
+  lanes_final_exponentiation(h, c, role);
+  if (i0 >= n) return;
+  const Fp6& r = role ? c.E.c1 : c.E.c0;
+  uint8_t* o = gt_out + i * 384 + role * 192;
+  fp2_store(o, r.c0);
+  fp2_store(o + 64, r.c1);
+  fp2_store(o + 128, r.c2);
 }
 
 }  // namespace sylow_kernels

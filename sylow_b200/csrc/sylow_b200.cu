@@ -1067,6 +1067,7 @@ struct sylow_b200_ctx {
   int* d_fail = nullptr;
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
   DevBuf tables, sum0, sum1, proj, msm;
+  DevBuf fexp_lanes[2];  // FexpCold records of k_final_exp_lanes, one buffer per compute stream (stream, stream2)
   unsigned glued_attr_mask = 0;
   // multi-device parent (sylow_b200_create_multi): owns one single-device context per GPU and nothing else
   std::vector<sylow_b200_ctx*> children;
@@ -1129,21 +1130,42 @@ static inline cudaStream_t pick(sylow_b200_ctx* ctx, void* stream) {
 // 0.6 wave is launched separately as one (k_final_exp) or two (k_miller) SMALL blocks per SM, so that every SM works
 // on it at low occupancy - a lone warp per scheduler runs 1.5x (Miller) to 2x (final exponentiation) faster than one of
 // two or three co-resident warps (profiles/r01_overlap_probe.md), and the remainder finishes in that much less time.
+#ifndef SY_TAIL_SPLIT_DEFAULT
+#define SY_TAIL_SPLIT_DEFAULT 1
+#endif
 struct WaveSplit {
   size_t n_main;       // items in whole waves (launched with the kernel's normal block size)
   size_t n_tail;       // remainder
   unsigned tail_threads, tail_blocks;
+  // SYLOW_B200_TAIL_SPLIT=2: the last whole wave and the remainder as two rounds of equal, reduced occupancy
+  size_t n_mid = 0;
+  unsigned mid_threads = 0, mid_blocks = 0;
 };
 static WaveSplit wave_split(const sylow_b200_ctx* ctx, size_t n, int threads, int blocks_per_sm) {
   WaveSplit w{n, 0, 0, 0};
   const size_t wave = (size_t)ctx->sms * threads * blocks_per_sm;
   const size_t r = n % wave;
-  static const int mode = [] {
-    const char* v = getenv("SYLOW_B200_TAIL_SPLIT");  // 0 disables (measurement)
-    return v ? atoi(v) : 1;
-  }();
-  if (!mode || r == 0 || r * 10 >= wave * 6) return w;
+  const char* v = getenv("SYLOW_B200_TAIL_SPLIT");  // 0 disables (measurement), 2: two equal rounds
+  const int mode = v ? atoi(v) : SY_TAIL_SPLIT_DEFAULT;
+  if (!mode || r == 0) return w;
   const size_t slots = (size_t)ctx->sms * blocks_per_sm;
+  if (mode == 2 && n > wave && r * 10 < wave * 8) {
+    // warps per block slot over the last 1 + r waves, cut into two rounds
+    const size_t rest = wave + r;
+    const unsigned warps = (unsigned)(((rest + slots - 1) / slots + 31) / 32);
+    const unsigned w1 = (warps + 1) / 2, w2 = warps - w1;
+    size_t n1 = slots * w1 * 32;
+    if (n1 > rest) n1 = rest;
+    w.n_main = n - rest;
+    w.n_mid = n1;
+    w.mid_threads = w1 * 32;
+    w.mid_blocks = (unsigned)((n1 + w.mid_threads - 1) / w.mid_threads);
+    w.n_tail = rest - n1;
+    w.tail_threads = w2 ? w2 * 32 : 32;
+    w.tail_blocks = (unsigned)((w.n_tail + w.tail_threads - 1) / w.tail_threads);
+    return w;
+  }
+  if (r * 10 >= wave * 6) return w;
   unsigned t = (unsigned)(((r + slots - 1) / slots + 31) / 32 * 32);
   if (t > (unsigned)threads) t = threads;
   w.n_main = n - r;
@@ -1152,16 +1174,56 @@ static WaveSplit wave_split(const sylow_b200_ctx* ctx, size_t n, int threads, in
   w.tail_blocks = (unsigned)((r + t - 1) / t);
   return w;
 }
+// Two lanes per pair (k_miller_lanes, csrc/pairing_lanes.cuh): the same values in about half the time per pair when
+// the pairs alone cannot fill the GPU.  Used for batches of at most one two-lane wave (148 x 128 pairs) and for the
+// remainder of a larger batch after its whole one-thread waves, when that remainder fits one two-lane wave.
+// SYLOW_B200_LANES: 0 never, 1 automatic (default), 2 always (measurement and the parity tests).
+static int lanes_mode() {  // read on every call (the tests flip it inside one process)
+  const char* v = getenv("SYLOW_B200_LANES");
+  return v ? atoi(v) : 1;
+}
+static int launch_miller_lanes(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
+                               const uint8_t* g2_inf, size_t n, uint8_t* f_out, int raw_out, cudaStream_t s) {
+  // spread a small batch over every SM: pairs per block = n / (2 blocks x SMs), in whole warps (16 pairs), at most 64
+  const size_t slots = (size_t)ctx->sms * SY_LANES_MINB;
+  size_t pairs = ((n + slots - 1) / slots + 15) / 16 * 16;
+  if (pairs > SY_LANES_THREADS / 2) pairs = SY_LANES_THREADS / 2;
+  const unsigned threads = (unsigned)pairs * 2;
+  k_miller_lanes<<<nblocks(n, (int)pairs), threads, SY_LANES_SMEM_BYTES(threads), s>>>(g1, g1_inf, g2, g2_inf, n, f_out,
+                                                                                      raw_out);
+  LAUNCHED(ctx);
+  return 0;
+}
 static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g1_inf, const uint8_t* g2,
                          const uint8_t* g2_inf, size_t n, uint8_t* f_out, int raw_out, cudaStream_t s) {
-  const WaveSplit w = wave_split(ctx, n, SY_MILLER_THREADS, SY_MILLER_MINB);
+  const int lanes = lanes_mode();
+  const size_t lane_wave = (size_t)ctx->sms * (SY_LANES_THREADS / 2) * SY_LANES_MINB;
+  if (lanes == 2 || (lanes == 1 && n <= lane_wave))
+    return launch_miller_lanes(ctx, g1, g1_inf, g2, g2_inf, n, f_out, raw_out, s);
+  WaveSplit w = wave_split(ctx, n, SY_MILLER_THREADS, SY_MILLER_MINB);
+  const size_t wave1 = (size_t)ctx->sms * SY_MILLER_THREADS * SY_MILLER_MINB;
+  if (lanes == 1 && n % wave1 && n % wave1 <= lane_wave) {
+    const size_t r = n % wave1, o = n - r;
+    k_miller<<<nblocks(o, SY_MILLER_THREADS), SY_MILLER_THREADS, SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS), s>>>(
+        g1, g1_inf, g2, g2_inf, 1, o, f_out, raw_out);
+    LAUNCHED(ctx);
+    return launch_miller_lanes(ctx, g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128,
+                               g2_inf ? g2_inf + o : nullptr, r, f_out + o * 384, raw_out, s);
+  }
   if (w.n_main) {
     k_miller<<<nblocks(w.n_main, SY_MILLER_THREADS), SY_MILLER_THREADS, SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS), s>>>(
         g1, g1_inf, g2, g2_inf, 1, w.n_main, f_out, raw_out);
     LAUNCHED(ctx);
   }
-  if (w.n_tail) {
+  if (w.n_mid) {
     const size_t o = w.n_main;
+    k_miller<<<w.mid_blocks, w.mid_threads, SY_MILLER_SMEM_BYTES(w.mid_threads), s>>>(
+        g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128, g2_inf ? g2_inf + o : nullptr, 1, w.n_mid,
+        f_out + o * 384, raw_out);
+    LAUNCHED(ctx);
+  }
+  if (w.n_tail) {
+    const size_t o = w.n_main + w.n_mid;
     k_miller<<<w.tail_blocks, w.tail_threads, SY_MILLER_SMEM_BYTES(w.tail_threads), s>>>(
         g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128, g2_inf ? g2_inf + o : nullptr, 1, w.n_tail,
         f_out + o * 384, raw_out);
@@ -1169,15 +1231,41 @@ static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* 
   }
   return 0;
 }
+// Two lanes per final exponentiation (k_final_exp_lanes): for batches that leave most schedulers without a warp even
+// at one warp each (at most SY_FEXP_LANES_MAX_PER_SM items per SM).
+#ifndef SY_FEXP_LANES_MAX_PER_SM
+#define SY_FEXP_LANES_MAX_PER_SM 64
+#endif
+static int launch_final_exp_lanes(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, size_t n, uint8_t* gt_out,
+                                  cudaStream_t s) {
+  const size_t slots = (size_t)ctx->sms * SY_LANES_MINB;
+  size_t pairs = ((n + slots - 1) / slots + 15) / 16 * 16;
+  if (pairs > SY_LANES_THREADS / 2) pairs = SY_LANES_THREADS / 2;
+  const unsigned threads = (unsigned)pairs * 2, blocks = nblocks(n, (int)pairs);
+  DevBuf& scratch = ctx->fexp_lanes[s == ctx->stream2 ? 1 : 0];
+  CKS(reserve(ctx, scratch, SY_FLANES_SCRATCH_BYTES((size_t)blocks * pairs)));
+  k_final_exp_lanes<<<blocks, threads, SY_FLANES_SMEM_BYTES(threads), s>>>(f, raw_in, n, gt_out, scratch.p);
+  LAUNCHED(ctx);
+  return 0;
+}
 static int launch_final_exp(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, size_t n, uint8_t* gt_out, cudaStream_t s) {
+  const int lanes = lanes_mode();
+  if (lanes == 2 || (lanes == 1 && n <= (size_t)ctx->sms * SY_FEXP_LANES_MAX_PER_SM))
+    return launch_final_exp_lanes(ctx, f, raw_in, n, gt_out, s);
   const WaveSplit w = wave_split(ctx, n, SY_FEXP_THREADS, SY_FEXP_MINB);
   if (w.n_main) {
     k_final_exp<<<nblocks(w.n_main, SY_FEXP_THREADS), SY_FEXP_THREADS, SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS), s>>>(
         f, raw_in, w.n_main, gt_out);
     LAUNCHED(ctx);
   }
-  if (w.n_tail) {
+  if (w.n_mid) {
     const size_t o = w.n_main;
+    k_final_exp<<<w.mid_blocks, w.mid_threads, SY_FEXP_SMEM_BYTES(w.mid_threads), s>>>(f + o * 384, raw_in, w.n_mid,
+                                                                                       gt_out + o * 384);
+    LAUNCHED(ctx);
+  }
+  if (w.n_tail) {
+    const size_t o = w.n_main + w.n_mid;
     k_final_exp<<<w.tail_blocks, w.tail_threads, SY_FEXP_SMEM_BYTES(w.tail_threads), s>>>(f + o * 384, raw_in, w.n_tail,
                                                                                          gt_out + o * 384);
     LAUNCHED(ctx);
@@ -1211,6 +1299,12 @@ int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
   if (e == cudaSuccess && SY_MILLER_SMEM)
     e = cudaFuncSetAttribute(k_miller, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_miller_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SY_LANES_SMEM_BYTES(SY_LANES_THREADS));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_final_exp_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SY_FLANES_SMEM_BYTES(SY_LANES_THREADS));
   if (e == cudaSuccess && SY_FEXP_SMEM)
     e = cudaFuncSetAttribute(k_final_exp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS));
@@ -1243,6 +1337,8 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->sum1.p) cudaFree(ctx->sum1.p);
   if (ctx->proj.p) cudaFree(ctx->proj.p);
   if (ctx->msm.p) cudaFree(ctx->msm.p);
+  for (DevBuf& b : ctx->fexp_lanes)
+    if (b.p) cudaFree(b.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);

@@ -8,7 +8,31 @@
 #include "../../sylow_b200/csrc/wire.cuh"
 #include "../../sylow_b200/csrc/hash.cuh"
 #include "../../sylow_b200/csrc/fr.cuh"
+#include "../../sylow_b200/csrc/pairing_lanes.cuh"
+#include <atomic>
 #include <cstring>
+#include <thread>
+
+// Two host threads stand in for the two lanes of pairing_lanes.cuh; SY_LANE_SYNC() is this barrier.
+namespace {
+struct LaneBarrier {
+  std::atomic<int> count{0};
+  std::atomic<int> phase{0};
+  void wait() {
+    int ph = phase.load();
+    if (count.fetch_add(1) == 1) {
+      count.store(0);
+      phase.store(ph + 1);
+    } else {
+      while (phase.load() == ph) std::this_thread::yield();
+    }
+  }
+};
+thread_local LaneBarrier* tl_barrier = nullptr;
+}  // namespace
+extern "C" void sylow_hostsim_lane_sync() {
+  if (tl_barrier) tl_barrier->wait();
+}
 
 using namespace sylow;
 
@@ -56,6 +80,38 @@ void hs_fp12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
 void hs_miller_loop(const uint8_t* g1, const uint8_t* g2, uint8_t* out) {
   Fp12 f = miller_loop(fp_load(g1), fp_load(g1 + 32), fp2_load(g2), fp2_load(g2 + 64));
   fp12_store(out, f);
+}
+// the two-lane Miller loop, one host thread per lane
+void hs_miller_loop_lanes(const uint8_t* g1, const uint8_t* g2, uint8_t* out) {
+  static PairSlot slot;
+  LaneBarrier bar;
+  Fp xp = fp_load(g1), yp = fp_load(g1 + 32);
+  Fp2 qx = fp2_load(g2), qy = fp2_load(g2 + 64);
+  auto lane = [&](int role) {
+    tl_barrier = &bar;
+    lanes_miller_loop(slot, role, xp, yp, qx, qy);
+    tl_barrier = nullptr;
+  };
+  std::thread t1(lane, 1);
+  lane(0);
+  t1.join();
+  fp12_store(out, slot.f);
+}
+// the two-lane final exponentiation, one host thread per lane
+void hs_final_exp_lanes(const uint8_t* f, uint8_t* out) {
+  static FexpHot hot;
+  static FexpCold cold;
+  LaneBarrier bar;
+  cold.f = fp12_load(f);
+  auto lane = [&](int role) {
+    tl_barrier = &bar;
+    lanes_final_exponentiation(hot, cold, role);
+    tl_barrier = nullptr;
+  };
+  std::thread t1(lane, 1);
+  lane(0);
+  t1.join();
+  fp12_store(out, cold.E);
 }
 // G2Affine::precompute: 87 triples, canonical, 16704 bytes
 void hs_g2_precompute(const uint8_t* g2, uint8_t* out) {

@@ -350,3 +350,60 @@ def test_glued_pairing_checks_large(eng):
         m = 64
         small = eng.pairing_check_batch(d_g1[: m * k].cpu().numpy(), d_g2[: m * k].cpu().numpy(), k, g1_inf=inf1[: m * k])
         assert (small == expect[:m]).all()
+
+
+# ------------------------------------------------------------------------- two lanes per Miller loop (pairing_lanes.cuh)
+def test_miller_lanes_match_one_thread_kernel(eng, monkeypatch):
+    """k_miller_lanes (two cooperating lanes per pair, SYLOW_B200_LANES=2) against k_miller (=0) and the oracle:
+    MillerLoopResult bit for bit, ragged sizes around the block and wave boundaries, infinity flags, and the automatic
+    policy (=1: small batches and wave remainders on two lanes) through pairing_batch."""
+    import torch
+
+    rng = random.Random(41)
+    dev = torch.device("cuda", 0)
+    n = 148 * 256 + 148 * 128 - 77  # one whole one-thread wave plus a remainder that fits one two-lane wave
+    rs = np.random.RandomState(6)
+    k = rs.randint(0, 256, size=(2 * n, 32), dtype=np.uint8)
+    k[:, 31] &= 0x1F
+    d_g1 = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    d_g2 = torch.empty((n, 128), dtype=torch.uint8, device=dev)
+    g1 = np.tile(np.frombuffer(w.g1_b(o.G1_GEN), np.uint8), (n, 1))
+    g2 = np.tile(np.frombuffer(w.g2_b(o.G2_GEN), np.uint8), (n, 1))
+    eng.g1_mul_batch_dev(torch.from_numpy(g1).to(dev), torch.from_numpy(k[:n]).to(dev), d_g1)
+    eng.g2_mul_batch_dev(torch.from_numpy(g2).to(dev), torch.from_numpy(k[n:]).to(dev), d_g2)
+    torch.cuda.synchronize()
+    H1, H2 = d_g1.cpu().numpy(), d_g2.cpu().numpy()
+    inf1 = np.zeros(n, dtype=np.uint8)
+    inf2 = np.zeros(n, dtype=np.uint8)
+    inf1[[3, 64, n - 1]] = 1
+    inf2[[5, 64, 1000]] = 1
+    res = {}
+    for mode in ("0", "2", "1"):
+        monkeypatch.setenv("SYLOW_B200_LANES", mode)
+        res[mode] = {m: eng.miller_loop_batch(H1[:m], H2[:m], inf1[:m], inf2[:m])
+                     for m in (1, 2, 15, 16, 17, 63, 64, 65, 150, 148 * 128 + 1, n)}
+    for m, a in res["0"].items():
+        assert np.array_equal(a, res["2"][m]), "two-lane kernel differs at n = %d" % m
+        assert np.array_equal(a, res["1"][m]), "automatic policy differs at n = %d" % m
+    full = res["2"][n]
+    for i in (0, 1, 2, 16, 63, 64, 65, 149, 148 * 128, n - 2):
+        if inf1[i] or inf2[i]:
+            continue
+        assert w.b_fp12(bytes(full[i])) == o.miller_loop(o.g2_precompute(w.b_g2(bytes(H2[i]))), w.b_g1(bytes(H1[i])))
+    for i in (3, 5, 64, 1000, n - 1):
+        assert w.b_fp12(bytes(full[i])) == o.FP12_ONE
+    # the two-lane final exponentiation against the one-thread kernel and the oracle
+    fx = {}
+    for mode in ("0", "2", "1"):
+        monkeypatch.setenv("SYLOW_B200_LANES", mode)
+        fx[mode] = {m: eng.final_exp_batch(res["0"][n][:m]) for m in (1, 2, 17, 64, 65, 150, 148 * 64 + 3)}
+    for m, a in fx["0"].items():
+        assert np.array_equal(a, fx["2"][m]), "two-lane final exponentiation differs at n = %d" % m
+        assert np.array_equal(a, fx["1"][m]), "automatic policy differs at n = %d" % m
+    for i in (0, 1, 149):
+        assert w.b_fp12(bytes(fx["2"][150][i])) == o.final_exponentiation(w.b_fp12(bytes(res["0"][n][i])))
+    # pairing_batch end to end under the automatic policy, small batch
+    monkeypatch.setenv("SYLOW_B200_LANES", "1")
+    gt = eng.pairing_batch(H1[:5], H2[:5])
+    for i in range(5):
+        assert w.b_fp12(bytes(gt[i])) == o.pairing_affine(w.b_g1(bytes(H1[i])), w.b_g2(bytes(H2[i])))

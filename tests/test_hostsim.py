@@ -22,7 +22,7 @@ def hs():
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["nvcc", "-x", "cu", "-O2", "-std=c++17", "-DSYLOW_HOSTSIM", "-shared", "-Xcompiler",
-                               "-fPIC", "-w", "-o", SO, src])
+                               "-fPIC,-pthread", "-w", "-o", SO, src])
     lib = ctypes.CDLL(SO)
     lib.hs_hash_to_g1.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p]
     lib.hs_hash_to_field.argtypes = lib.hs_hash_to_g1.argtypes
@@ -146,6 +146,25 @@ def test_miller_and_final_exp_random(hs):
     out2 = ctypes.create_string_buffer(384)
     hs.hs_final_exp(out.raw, out2)
     assert w.b_fp12(out2.raw) == o.final_exponentiation(f)
+
+
+def test_miller_loop_two_lanes(hs):
+    """pairing_lanes.cuh: two cooperating lanes (two host threads here) produce the one-thread MillerLoopResult."""
+    rng = random.Random(33)
+    for p, q in [(o.G1_GEN, o.G2_GEN)] + [(w.rand_g1(rng), w.rand_g2(rng)) for _ in range(2)]:
+        out = ctypes.create_string_buffer(384)
+        hs.hs_miller_loop_lanes(w.g1_b(p), w.g2_b(q), out)
+        assert w.b_fp12(out.raw) == o.miller_loop(o.g2_precompute(q), p)
+
+
+def test_final_exponentiation_two_lanes(hs):
+    """pairing_lanes.cuh: the two-lane final exponentiation against the oracle (and so against the one-thread chain)."""
+    rng = random.Random(34)
+    p, q = w.rand_g1(rng), w.rand_g2(rng)
+    for f in (o.miller_loop(o.g2_precompute(q), p), o.miller_loop(o.g2_precompute(o.G2_GEN), o.G1_GEN), w.rand_fp12(rng)):
+        out = ctypes.create_string_buffer(384)
+        hs.hs_final_exp_lanes(w.fp12_b(f), out)
+        assert w.b_fp12(out.raw) == o.final_exponentiation(f)
 
 
 def test_scalar_mul(hs, kats):
