@@ -402,6 +402,21 @@ def main():
                                  % (args.log2n, world, world),
               "waves_per_gpu": {"k_miller": ns / (sms * 256.0), "k_final_exp": ns / (sms * 384.0)}}
 
+    # ---- batches too small to fill the GPU with one thread per pairing: the two-lane kernels (csrc/pairing_lanes.cuh)
+    # against the one-thread kernels on the same inputs (the library reads SYLOW_B200_LANES on every call)
+    small = {"unit": "ms per batch", "note": "pairing_batch_dev; two lanes per Miller loop / final exponentiation when "
+             "the batch fits one two-lane wave (148 x 128 items), and for wave remainders of larger batches"}
+    for m in (1, 1024, 9472, 18944):
+        row = {}
+        for key, mode in (("two_lanes", None), ("one_thread", "0")):
+            if mode is None:
+                os.environ.pop("SYLOW_B200_LANES", None)
+            else:
+                os.environ["SYLOW_B200_LANES"] = mode
+            row[key] = time_ms(lambda: eng.pairing_batch_dev(d_g1[:m], d_g2[:m], d_out[:m]), reps=5)
+        os.environ.pop("SYLOW_B200_LANES", None)
+        small[str(m)] = row
+
     # ---- cross-rank parity checks (cheap; every N): run BEFORE the long legs so a wrong build fails early
     parity = {}
     m_chk = min(2048, ns)
@@ -669,6 +684,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roof,
             "strong": strong,
+            "small_batches": small,
             "parity_checks": parity,
             "reference_published": PUBLISHED,
         }

@@ -174,6 +174,27 @@ k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
   ok[c] = one ? 1 : 0;
 }
 
+// The two halves of k_check_products as kernels of their own, around k_final_exp_lanes for small batches:
+// out[c] = prod_{j<k} f[c*k + j] (Montgomery form), and ok[c] = (gt[c] == 1) on canonical values.
+__global__ void k_group_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* out_raw) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_checks) return;
+  Fp12 acc = fp12_load_raw(f_raw + c * k * 384);
+  for (size_t j = 1; j < k; j++) acc = fp12_mul(acc, fp12_load_raw(f_raw + (c * k + j) * 384));
+  fp12_store_raw(out_raw + c * 384, acc);
+}
+__global__ void k_gt_is_one(const uint8_t* gt, size_t n, uint8_t* ok) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const uint4* p = reinterpret_cast<const uint4*>(gt + c * 384);
+  uint32_t d = 0;
+  for (int i = 0; i < 24; i++) {
+    uint4 v = p[i];
+    d |= (i == 0 ? v.x ^ 1u : v.x) | v.y | v.z | v.w;
+  }
+  ok[c] = d == 0 ? 1 : 0;
+}
+
 SY_HD void g1_store_proj(uint8_t* p, const G1Proj& q) {
   fp_store_raw(p, q.x);
   fp_store_raw(p + 32, q.y);
@@ -1067,6 +1088,7 @@ struct sylow_b200_ctx {
   int* d_fail = nullptr;
   uint8_t* d_gen_table = nullptr;  // G2PreComputed of the G2 generator, Montgomery form (16704 B)
   DevBuf tables, sum0, sum1, proj, msm;
+  DevBuf check_stage[2];  // group products / Gt values of launch_check_products' two-lane path, per compute stream
   DevBuf fexp_lanes[2];  // FexpCold records of k_final_exp_lanes, one buffer per compute stream (stream, stream2)
   unsigned glued_attr_mask = 0;
   // multi-device parent (sylow_b200_create_multi): owns one single-device context per GPU and nothing else
@@ -1130,42 +1152,21 @@ static inline cudaStream_t pick(sylow_b200_ctx* ctx, void* stream) {
 // 0.6 wave is launched separately as one (k_final_exp) or two (k_miller) SMALL blocks per SM, so that every SM works
 // on it at low occupancy - a lone warp per scheduler runs 1.5x (Miller) to 2x (final exponentiation) faster than one of
 // two or three co-resident warps (profiles/r01_overlap_probe.md), and the remainder finishes in that much less time.
-#ifndef SY_TAIL_SPLIT_DEFAULT
-#define SY_TAIL_SPLIT_DEFAULT 1
-#endif
 struct WaveSplit {
   size_t n_main;       // items in whole waves (launched with the kernel's normal block size)
   size_t n_tail;       // remainder
   unsigned tail_threads, tail_blocks;
-  // SYLOW_B200_TAIL_SPLIT=2: the last whole wave and the remainder as two rounds of equal, reduced occupancy
-  size_t n_mid = 0;
-  unsigned mid_threads = 0, mid_blocks = 0;
 };
+// (Cutting the last 1 + r waves into two rounds of equal, reduced occupancy instead was measured and is not better:
+// profiles/r02g_policy_sweep.jsonl, tail_split 2.)
 static WaveSplit wave_split(const sylow_b200_ctx* ctx, size_t n, int threads, int blocks_per_sm) {
   WaveSplit w{n, 0, 0, 0};
   const size_t wave = (size_t)ctx->sms * threads * blocks_per_sm;
   const size_t r = n % wave;
-  const char* v = getenv("SYLOW_B200_TAIL_SPLIT");  // 0 disables (measurement), 2: two equal rounds
-  const int mode = v ? atoi(v) : SY_TAIL_SPLIT_DEFAULT;
-  if (!mode || r == 0) return w;
+  const char* v = getenv("SYLOW_B200_TAIL_SPLIT");  // 0 disables (measurement)
+  const int mode = v ? atoi(v) : 1;
+  if (!mode || r == 0 || r * 10 >= wave * 6) return w;
   const size_t slots = (size_t)ctx->sms * blocks_per_sm;
-  if (mode == 2 && n > wave && r * 10 < wave * 8) {
-    // warps per block slot over the last 1 + r waves, cut into two rounds
-    const size_t rest = wave + r;
-    const unsigned warps = (unsigned)(((rest + slots - 1) / slots + 31) / 32);
-    const unsigned w1 = (warps + 1) / 2, w2 = warps - w1;
-    size_t n1 = slots * w1 * 32;
-    if (n1 > rest) n1 = rest;
-    w.n_main = n - rest;
-    w.n_mid = n1;
-    w.mid_threads = w1 * 32;
-    w.mid_blocks = (unsigned)((n1 + w.mid_threads - 1) / w.mid_threads);
-    w.n_tail = rest - n1;
-    w.tail_threads = w2 ? w2 * 32 : 32;
-    w.tail_blocks = (unsigned)((w.n_tail + w.tail_threads - 1) / w.tail_threads);
-    return w;
-  }
-  if (r * 10 >= wave * 6) return w;
   unsigned t = (unsigned)(((r + slots - 1) / slots + 31) / 32 * 32);
   if (t > (unsigned)threads) t = threads;
   w.n_main = n - r;
@@ -1174,9 +1175,11 @@ static WaveSplit wave_split(const sylow_b200_ctx* ctx, size_t n, int threads, in
   w.tail_blocks = (unsigned)((r + t - 1) / t);
   return w;
 }
-// Two lanes per pair (k_miller_lanes, csrc/pairing_lanes.cuh): the same values in about half the time per pair when
-// the pairs alone cannot fill the GPU.  Used for batches of at most one two-lane wave (148 x 128 pairs) and for the
-// remainder of a larger batch after its whole one-thread waves, when that remainder fits one two-lane wave.
+// Two lanes per item (k_miller_lanes, k_final_exp_lanes, csrc/pairing_lanes.cuh): the same values in 0.55-0.6 of the
+// time per item when the items alone cannot fill the GPU, 0.88 of the one-thread kernels' throughput when they can
+// (profiles/r02f_lanes_kbench.jsonl, r02g_policy_sweep.jsonl).  Used for batches of at most one two-lane wave
+// (148 x 128 items) and for the remainder of a larger batch after its whole one-thread waves when that remainder fits one
+// two-lane wave: 1 .. 9 472 pairings 8.5 -> 5.0 ms, 2^17 pairings (a 2^20 batch over 8 GPUs) 46.3 -> 44.3 ms.
 // SYLOW_B200_LANES: 0 never, 1 automatic (default), 2 always (measurement and the parity tests).
 static int lanes_mode() {  // read on every call (the tests flip it inside one process)
   const char* v = getenv("SYLOW_B200_LANES");
@@ -1215,15 +1218,8 @@ static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* 
         g1, g1_inf, g2, g2_inf, 1, w.n_main, f_out, raw_out);
     LAUNCHED(ctx);
   }
-  if (w.n_mid) {
-    const size_t o = w.n_main;
-    k_miller<<<w.mid_blocks, w.mid_threads, SY_MILLER_SMEM_BYTES(w.mid_threads), s>>>(
-        g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128, g2_inf ? g2_inf + o : nullptr, 1, w.n_mid,
-        f_out + o * 384, raw_out);
-    LAUNCHED(ctx);
-  }
   if (w.n_tail) {
-    const size_t o = w.n_main + w.n_mid;
+    const size_t o = w.n_main;
     k_miller<<<w.tail_blocks, w.tail_threads, SY_MILLER_SMEM_BYTES(w.tail_threads), s>>>(
         g1 + o * 64, g1_inf ? g1_inf + o : nullptr, g2 + o * 128, g2_inf ? g2_inf + o : nullptr, 1, w.n_tail,
         f_out + o * 384, raw_out);
@@ -1231,11 +1227,6 @@ static int launch_miller(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* 
   }
   return 0;
 }
-// Two lanes per final exponentiation (k_final_exp_lanes): for batches that leave most schedulers without a warp even
-// at one warp each (at most SY_FEXP_LANES_MAX_PER_SM items per SM).
-#ifndef SY_FEXP_LANES_MAX_PER_SM
-#define SY_FEXP_LANES_MAX_PER_SM 64
-#endif
 static int launch_final_exp_lanes(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, size_t n, uint8_t* gt_out,
                                   cudaStream_t s) {
   const size_t slots = (size_t)ctx->sms * SY_LANES_MINB;
@@ -1250,26 +1241,53 @@ static int launch_final_exp_lanes(sylow_b200_ctx* ctx, const uint8_t* f, int raw
 }
 static int launch_final_exp(sylow_b200_ctx* ctx, const uint8_t* f, int raw_in, size_t n, uint8_t* gt_out, cudaStream_t s) {
   const int lanes = lanes_mode();
-  if (lanes == 2 || (lanes == 1 && n <= (size_t)ctx->sms * SY_FEXP_LANES_MAX_PER_SM))
-    return launch_final_exp_lanes(ctx, f, raw_in, n, gt_out, s);
+  const size_t lane_wave = (size_t)ctx->sms * (SY_LANES_THREADS / 2) * SY_LANES_MINB;
+  if (lanes == 2 || (lanes == 1 && n <= lane_wave)) return launch_final_exp_lanes(ctx, f, raw_in, n, gt_out, s);
+  const size_t wave1 = (size_t)ctx->sms * SY_FEXP_THREADS * SY_FEXP_MINB;
+  if (lanes == 1 && n % wave1 && n % wave1 <= lane_wave) {
+    const size_t r = n % wave1, o = n - r;
+    k_final_exp<<<nblocks(o, SY_FEXP_THREADS), SY_FEXP_THREADS, SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS), s>>>(f, raw_in, o,
+                                                                                                       gt_out);
+    LAUNCHED(ctx);
+    return launch_final_exp_lanes(ctx, f + o * 384, raw_in, r, gt_out + o * 384, s);
+  }
   const WaveSplit w = wave_split(ctx, n, SY_FEXP_THREADS, SY_FEXP_MINB);
   if (w.n_main) {
     k_final_exp<<<nblocks(w.n_main, SY_FEXP_THREADS), SY_FEXP_THREADS, SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS), s>>>(
         f, raw_in, w.n_main, gt_out);
     LAUNCHED(ctx);
   }
-  if (w.n_mid) {
-    const size_t o = w.n_main;
-    k_final_exp<<<w.mid_blocks, w.mid_threads, SY_FEXP_SMEM_BYTES(w.mid_threads), s>>>(f + o * 384, raw_in, w.n_mid,
-                                                                                       gt_out + o * 384);
-    LAUNCHED(ctx);
-  }
   if (w.n_tail) {
-    const size_t o = w.n_main + w.n_mid;
+    const size_t o = w.n_main;
     k_final_exp<<<w.tail_blocks, w.tail_threads, SY_FEXP_SMEM_BYTES(w.tail_threads), s>>>(f + o * 384, raw_in, w.n_tail,
                                                                                          gt_out + o * 384);
     LAUNCHED(ctx);
   }
+  return 0;
+}
+
+// ok[c] = final_exp(prod_{j<k} f[c*k + j]) == 1 for the Montgomery-form Miller values at f.  Batches that fit one
+// two-lane wave go through k_final_exp_lanes (group products, exponentiation, comparison as three launches: about half
+// the latency); larger ones through the fused one-thread kernel, in blocks small enough to reach every SM.
+static int launch_check_products(sylow_b200_ctx* ctx, const uint8_t* f, size_t k, size_t n_checks, uint8_t* ok,
+                                 cudaStream_t s) {
+  const size_t lane_wave = (size_t)ctx->sms * (SY_LANES_THREADS / 2) * SY_LANES_MINB;
+  if (lanes_mode() != 0 && n_checks <= lane_wave) {
+    DevBuf& stage = ctx->check_stage[s == ctx->stream2 ? 1 : 0];
+    CKS(reserve(ctx, stage, n_checks * 384));
+    if (k > 1) {
+      k_group_products<<<nblocks(n_checks, 32), 32, 0, s>>>(f, k, n_checks, stage.p);
+      LAUNCHED(ctx);
+    }
+    CKS(launch_final_exp_lanes(ctx, k > 1 ? stage.p : f, 1, n_checks, stage.p, s));
+    k_gt_is_one<<<nblocks(n_checks, SY_SMALL_THREADS), SY_SMALL_THREADS, 0, s>>>(stage.p, n_checks, ok);
+    LAUNCHED(ctx);
+    return 0;
+  }
+  unsigned t = (unsigned)(((n_checks + ctx->sms - 1) / ctx->sms + 31) / 32 * 32);
+  if (t > SY_FEXP_THREADS) t = SY_FEXP_THREADS;
+  k_check_products<<<nblocks(n_checks, (int)t), t, 0, s>>>(f, k, n_checks, ok);
+  LAUNCHED(ctx);
   return 0;
 }
 
@@ -1338,6 +1356,8 @@ int sylow_b200_destroy(sylow_b200_ctx* ctx) {
   if (ctx->proj.p) cudaFree(ctx->proj.p);
   if (ctx->msm.p) cudaFree(ctx->msm.p);
   for (DevBuf& b : ctx->fexp_lanes)
+    if (b.p) cudaFree(b.p);
+  for (DevBuf& b : ctx->check_stage)
     if (b.p) cudaFree(b.p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -1541,9 +1561,7 @@ int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, c
       CKS(launch_miller(ctx, g1, g1_inf, g2, g2_inf, n, ctx->scratch0.p, 1, s));
     }
   }
-  k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, k_prod, n_checks, ok_out);
-  LAUNCHED(ctx);
-  return 0;
+  return launch_check_products(ctx, ctx->scratch0.p, k_prod, n_checks, ok_out, s);
 }
 
 // batches from this size on convert to affine coordinates with one inversion per eight points
@@ -2322,8 +2340,7 @@ int sylow_b200_verify_each(sylow_b200_ctx* ctx, const uint8_t* pks, const uint8_
   CKS(to_dev(ctx, ctx->flag_b, sigs_inf, n, &dsgi));
   CKS(verify_miller_values(ctx, dpk, dpki, dm, dof, dsg, dsgi, n, dp, ctx->stream));
   CKS(reserve(ctx, ctx->out, n));
-  k_check_products<<<nblocks(n, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, ctx->stream>>>(ctx->scratch0.p, 1, n, ctx->out.p);
-  LAUNCHED(ctx);
+  CKS(launch_check_products(ctx, ctx->scratch0.p, 1, n, ctx->out.p, ctx->stream));
   CK(cudaMemcpyAsync(ok_out, ctx->out.p, n, cudaMemcpyDeviceToHost, ctx->stream));
   return check_hash_fail(ctx);
 }
@@ -2393,9 +2410,7 @@ int sylow_b200_pairing_check_fixed_batch_dev(sylow_b200_ctx* ctx, const uint8_t*
   else
     return SYLOW_B200_ERR_ARG;  // other shapes: use sylow_b200_pairing_check_batch
   CKS(st);
-  k_check_products<<<nblocks(n_checks, SY_FEXP_THREADS), SY_FEXP_THREADS, 0, s>>>(ctx->scratch0.p, 1, n_checks, d_ok_out);
-  LAUNCHED(ctx);
-  return 0;
+  return launch_check_products(ctx, ctx->scratch0.p, 1, n_checks, d_ok_out, s);
 }
 
 int sylow_b200_tables_to_device(sylow_b200_ctx* ctx, const uint8_t* coeffs, size_t k, uint8_t* d_tables_out, void* stream) {

@@ -2,7 +2,7 @@
 """Time the Miller-loop and final-exponentiation launches of one GPU for batch sizes around the wave boundaries under
 the launch policies of sylow_b200.cu (read per call from the environment):
   SYLOW_B200_LANES      0 one thread per item only, 1 automatic, 2 two lanes per item always
-  SYLOW_B200_TAIL_SPLIT 0 plain launches, 1 low-occupancy launch of the remainder, 2 last 1 + r waves as two equal rounds
+  SYLOW_B200_TAIL_SPLIT 0 plain launches, 1 low-occupancy launch of the remainder, (2 = last 1 + r waves as two equal rounds: measured in r02g, not better, removed)
 Prints one JSON line per policy: ms per call of miller_loop_batch_dev / final_exp_batch_dev / pairing_batch_dev."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
