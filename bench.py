@@ -13,6 +13,8 @@ region).  The inputs (192 MiB) and outputs (384 MiB) are larger than the 126 MB 
 Beside the headline the same JSON line carries
   * `strong`: ONE 2^20 batch sharded over the N ranks (BASELINE configs[1] as written), with its efficiency
     against N times the single-GPU rate;
+  * `small_batches`: batches that cannot fill the GPU with one thread per pairing, with the two-lane kernels
+    (csrc/pairing_lanes.cuh) and with the one-thread kernels only;
   * `verify_batch` (BASELINE configs[2], the other half of the metric): BLS verifies/s at 2^20 distinct signers
     per GPU - device-resident `value`, host-buffer `e2e` through sylow_b200_verify_batch (>= 5 repetitions), the
     random-weight (sound per signature) form beside the reference example's unweighted product, its own

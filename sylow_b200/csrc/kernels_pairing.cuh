@@ -8,8 +8,17 @@
 #ifndef SY_MILLER_THREADS
 #define SY_MILLER_THREADS 128
 #endif
+// Three 128-thread blocks per SM at 168 registers run one plain launch of 2^20 pairs 1 % faster (164.4 against 166.2 ms,
+// profiles/r02h_kbench.jsonl) but lose it again in the library, where the wave remainders run at low occupancy
+// (2^20: 167.6 against 166.0 ms, 2^17: 22.3 against 21.6 ms, profiles/r02i_policy_sweep_m128x3.jsonl): two blocks stay.
 #ifndef SY_MILLER_MINB
 #define SY_MILLER_MINB 2
+#endif
+#ifndef SY_GLUED_THREADS
+#define SY_GLUED_THREADS 128
+#endif
+#ifndef SY_GLUED_MINB
+#define SY_GLUED_MINB 2
 #endif
 #ifndef SY_FEXP_THREADS
 #define SY_FEXP_THREADS 384

@@ -57,7 +57,7 @@ struct DstPrime {
 };
 
 // coeffs[i] = G2Affine::precompute(g2[i]): 87 triples (c0, c1, c2), 16704 B per point, Montgomery (raw) or canonical
-__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
+__global__ void __launch_bounds__(SY_GLUED_THREADS, SY_GLUED_MINB)
 k_g2_precompute(const uint8_t* __restrict__ g2, size_t n, uint8_t* __restrict__ coeffs, int raw_out) {
   size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = i0 < n ? i0 : n - 1;
@@ -93,7 +93,7 @@ __global__ void k_fp_convert(const uint8_t* in, size_t n, uint8_t* out, int to_m
 // The NF tables (87 * 192 B each, Montgomery form) are staged once per block in shared memory; every
 // thread of a warp then reads the same triple (broadcast, conflict-free).
 template <int NV, int NF>
-__global__ void __launch_bounds__(SY_MILLER_THREADS, SY_MILLER_MINB)
+__global__ void __launch_bounds__(SY_GLUED_THREADS, SY_GLUED_MINB)
 k_glued(const uint8_t* __restrict__ g1v, size_t sv, const uint8_t* __restrict__ g1v_inf, const uint8_t* __restrict__ g2v,
         const uint8_t* __restrict__ g2v_inf, const uint8_t* __restrict__ g1f, size_t sf,
         const uint8_t* __restrict__ g1f_inf, const uint8_t* __restrict__ tables, size_t n,
@@ -1550,7 +1550,7 @@ int sylow_b200_pairing_check_batch_dev(sylow_b200_ctx* ctx, const uint8_t* g1, c
     CKS(reserve(ctx, ctx->scratch0, n * 384));
     // 2- and 4-pair checks (ecPairing, Groth16 without fixed tables) as ONE glued loop per check: one Fp12 squaring per
     // digit for all pairs of the check, like glued_miller_loop (pairing.rs:970-1022); needs enough checks to fill the GPU
-    const size_t wave = (size_t)ctx->sms * SY_MILLER_THREADS * SY_MILLER_MINB;
+    const size_t wave = (size_t)ctx->sms * SY_GLUED_THREADS * SY_GLUED_MINB;
     if (k == 2 && n_checks >= wave) {
       CKS((launch_glued<2, 0>(ctx, g1, 2, g1_inf, g2, g2_inf, nullptr, 0, nullptr, nullptr, n_checks, ctx->scratch0.p, s)));
       k_prod = 1;
@@ -1684,13 +1684,13 @@ static int launch_glued(sylow_b200_ctx* ctx, const uint8_t* g1v, size_t sv, cons
                         const uint8_t* g2v_inf, const uint8_t* g1f, size_t sf, const uint8_t* g1f_inf,
                         const uint8_t* tables, size_t n, uint8_t* f_out, cudaStream_t s) {
   // the opt-in for > 48 KB of dynamic shared memory is per device: remember it per context
-  size_t smem = (size_t)NF * SY_TABLE_BYTES + SY_MILLER_SMEM_BYTES(SY_MILLER_THREADS);
+  size_t smem = (size_t)NF * SY_TABLE_BYTES + SY_MILLER_SMEM_BYTES(SY_GLUED_THREADS);
   unsigned bit = 1u << (NV * 4 + NF);
   if (!(ctx->glued_attr_mask & bit)) {
     CK(cudaFuncSetAttribute(k_glued<NV, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->glued_attr_mask |= bit;
   }
-  k_glued<NV, NF><<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, smem, s>>>(g1v, sv, g1v_inf, g2v, g2v_inf, g1f, sf,
+  k_glued<NV, NF><<<nblocks(n, SY_GLUED_THREADS), SY_GLUED_THREADS, smem, s>>>(g1v, sv, g1v_inf, g2v, g2v_inf, g1f, sf,
                                                                               g1f_inf, tables, n, f_out);
   LAUNCHED(ctx);
   return 0;
@@ -1824,7 +1824,7 @@ static int verify_partial_core(sylow_b200_ctx* ctx, const uint8_t* d_pks, const 
     // fewest wave-times: whole waves of n / g threads (256 resident per SM) times the multiplications of g glued pairs.
     // Measured at 2^20 signatures (profiles/r02_verify_glue.jsonl): 192.4 / 171.2 / 163.3 ms for 1 / 2 / 4; at 2^13 the
     // order reverses (9.3 / 12.4 / 18.4 ms: a quarter of the threads, each four times as long).
-    const size_t wave = (size_t)ctx->sms * SY_MILLER_THREADS * SY_MILLER_MINB;
+    const size_t wave = (size_t)ctx->sms * SY_GLUED_THREADS * SY_GLUED_MINB;
     const size_t cost[3] = {8444, 2 * 8444 - 2268, 4 * 8444 - 3 * 2268};
     size_t best = ~(size_t)0;
     for (int j = 0; j < 3; j++) {
@@ -1916,7 +1916,8 @@ static int pairing_host(sylow_b200_ctx* ctx, const uint8_t* g1, const uint8_t* g
   CKS(to_dev(ctx, ctx->flag_b, g2_inf, n, &d2i));
   if (d1i || d2i) CK(cudaStreamSynchronize(ctx->stream));  // the flags are read from both compute streams
   // whole waves of both kernels: a multiple of the threads each of them keeps resident per SM
-  const size_t chunk = (size_t)ctx->sms * sy_lcm(SY_MILLER_THREADS * SY_MILLER_MINB, SY_FEXP_THREADS * SY_FEXP_MINB) * 2;
+  const size_t chunk =
+      (size_t)ctx->sms * sy_lcm(sy_lcm(SY_MILLER_THREADS * SY_MILLER_MINB, SY_FEXP_THREADS * SY_FEXP_MINB), 768) * 2;
   const size_t n_chunks = n <= 2 * chunk ? 1 : (n + chunk - 1) / chunk;
   const size_t step = n_chunks == 1 ? n : chunk;
   std::vector<cudaEvent_t> ev(2 * n_chunks, nullptr);
@@ -2353,7 +2354,7 @@ int sylow_b200_g2_precompute(sylow_b200_ctx* ctx, const uint8_t* g2, size_t n, u
   const uint8_t* d2;
   CKS(to_dev(ctx, ctx->in_b, g2, n * 128, &d2));
   CKS(reserve(ctx, ctx->out, n * SY_TABLE_BYTES));
-  k_g2_precompute<<<nblocks(n, SY_MILLER_THREADS), SY_MILLER_THREADS, 0, ctx->stream>>>(d2, n, ctx->out.p, 0);
+  k_g2_precompute<<<nblocks(n, SY_GLUED_THREADS), SY_GLUED_THREADS, 0, ctx->stream>>>(d2, n, ctx->out.p, 0);
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(coeffs_out, ctx->out.p, n * SY_TABLE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
   return finish(ctx);

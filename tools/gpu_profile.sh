@@ -17,8 +17,8 @@ one() {  # name regex skip count
   gzip -f gpurun_out/${tag}_src_$1.csv
   rm -f /tmp/${tag}_$1.ncu-rep
 }
-one k_miller 'k_miller' 1 1
-one k_final_exp 'k_final_exp' 2 2
+one k_miller 'k_miller$' 1 1
+one k_final_exp 'k_final_exp$' 2 2
 one k_hash_to_g1 'k_hash_to_g1' 2 1
 one k_glued13 'k_glued' 3 1
 one k_glued40 'k_glued' 4 1
