@@ -275,7 +275,7 @@ SY_HD_NOINLINE Fp12 fp12_inv(const Fp12& a) {
 #define SY_SPARSE_INPLACE 1
 #endif
 #if SY_SPARSE_INPLACE
-// In place: the four products that need sums of z first, then every slot is overwritten as soon as its last reader is
+// In place (x0, x2, x4 must not alias f): the four products that need sums of z first, then every slot is overwritten as soon as its last reader is
 // done (z0 after z1 x2, z2 after z3 x4, z1 after z5 x4, z3 after z3 x0, z4 and z5 after z5 x2) - no result record and
 // no copy back (the one-record form stored the six outputs to the frame, re-loaded them and wrote f word by word).
 SY_HD_NOINLINE void fp12_sparse_mul_assign(Fp12& f, const Fp2& x0, const Fp2& x4 /*ell_vw*/, const Fp2& x2 /*ell_vv*/) {
