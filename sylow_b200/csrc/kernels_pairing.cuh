@@ -30,13 +30,14 @@
 // Shared-memory slot of one thread's hot Fp12 accumulator: 384 bytes padded to 400, so that the eight lanes of a
 // 128-bit shared-memory access phase fall into different banks (100 words x lane = 4 x lane mod 32).
 // Measured at 2^20 (profiles/r02_kbench_*.jsonl): the Miller loop with its accumulator f in shared memory 170.0 ->
-// 166.1 ms (and no register spills left); the final exponentiation's running value in shared memory: no change
-// (174.6 / 174.7 ms), so it stays in the local frame; the Miller loop's G2 point in shared memory as well: slower (169.6).
+// 166.1 ms (and no register spills left); the Miller loop's G2 point in shared memory as well: slower (169.6).  The final
+// exponentiation's running value in shared memory made no difference while the Granger-Scott squaring still copied it
+// (174.6 / 174.7 ms); with the in-place squaring it does: 160.6 -> 158.1 ms (profiles/r02v_kbench_fexp_smem.jsonl).
 #ifndef SY_MILLER_SMEM
 #define SY_MILLER_SMEM 1
 #endif
 #ifndef SY_FEXP_SMEM
-#define SY_FEXP_SMEM 0
+#define SY_FEXP_SMEM 1
 #endif
 #define SY_ACC_STRIDE 400
 // Two lanes per Miller loop (pairing_lanes.cuh): one PairSlot (1 024 bytes) per lane pair, padded to 1 040 so that

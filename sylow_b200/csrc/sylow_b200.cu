@@ -169,7 +169,8 @@ k_check_products(const uint8_t* f_raw, size_t k, size_t n_checks, uint8_t* ok) {
     Fp12 v = fp12_load_raw(f_raw + (c * k + j) * 384);
     acc = j == 0 ? v : fp12_mul(acc, v);
   }
-  bool one = fp12_eq(final_exponentiation(acc), fp12_one());
+  final_exponentiation_assign(acc, SY_FEXP_SMEM ? acc_slot() : nullptr);
+  bool one = fp12_eq(acc, fp12_one());
   if (c0 >= n_checks) return;
   ok[c] = one ? 1 : 0;
 }
@@ -1286,7 +1287,7 @@ static int launch_check_products(sylow_b200_ctx* ctx, const uint8_t* f, size_t k
   }
   unsigned t = (unsigned)(((n_checks + ctx->sms - 1) / ctx->sms + 31) / 32 * 32);
   if (t > SY_FEXP_THREADS) t = SY_FEXP_THREADS;
-  k_check_products<<<nblocks(n_checks, (int)t), t, 0, s>>>(f, k, n_checks, ok);
+  k_check_products<<<nblocks(n_checks, (int)t), t, SY_FEXP_SMEM_BYTES(t), s>>>(f, k, n_checks, ok);
   LAUNCHED(ctx);
   return 0;
 }
@@ -1325,6 +1326,9 @@ int sylow_b200_create(sylow_b200_ctx** out, int device_id) {
                              (int)SY_FLANES_SMEM_BYTES(SY_LANES_THREADS));
   if (e == cudaSuccess && SY_FEXP_SMEM)
     e = cudaFuncSetAttribute(k_final_exp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS));
+  if (e == cudaSuccess && SY_FEXP_SMEM)
+    e = cudaFuncSetAttribute(k_check_products, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SY_FEXP_SMEM_BYTES(SY_FEXP_THREADS));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fail, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_fail, 0, sizeof(int));
