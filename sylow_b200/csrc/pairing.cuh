@@ -207,12 +207,10 @@ SY_HD void fp4_square(const Fp2& a, const Fp2& b, Fp2& c0, Fp2& c1) {
 }
 
 // Granger-Scott (pairing.rs:309-346)
-#ifndef SY_CYCLO_INPLACE
-#define SY_CYCLO_INPLACE 1
-#endif
-#if SY_CYCLO_INPLACE
 // In place, pair by pair: no copies of the six coefficients and no assembled result (the three Fp4 squarings read
 // disjoint pairs, and each pair's outputs only need that pair's - or, for the third, the second pair's - old values).
+// The form that copied z0..z5 into locals and assigned a result record cost 104 scalar spill stores, 105 reloads and 48
+// vector copies per call at 168 registers: k_final_exp 173.9 -> 160.5 ms per 2^20 (profiles/r02s_kbench_inplace.jsonl).
 SY_HD_NOINLINE void cyclotomic_square_assign(Fp12& f) {
   Fp2 &z0 = f.c0.c0, &z4 = f.c0.c1, &z3 = f.c0.c2, &z2 = f.c1.c0, &z1 = f.c1.c1, &z5 = f.c1.c2;
   Fp2 t0, t1, t2, t3;
@@ -227,29 +225,6 @@ SY_HD_NOINLINE void cyclotomic_square_assign(Fp12& f) {
   z2 = fp2_add(fp2_dbl(fp2_add(t0, z2)), t0);
   z3 = fp2_add(fp2_dbl(fp2_sub(t2, z3)), t2);
 }
-#else
-SY_HD_NOINLINE void cyclotomic_square_assign(Fp12& f) {
-  Fp2 z0 = f.c0.c0, z4 = f.c0.c1, z3 = f.c0.c2, z2 = f.c1.c0, z1 = f.c1.c1, z5 = f.c1.c2;
-  Fp2 t0, t1, t2, t3;
-  fp4_square(z0, z1, t0, t1);
-  z0 = fp2_sub(t0, z0);
-  z0 = fp2_add(fp2_dbl(z0), t0);
-  z1 = fp2_add(t1, z1);
-  z1 = fp2_add(fp2_dbl(z1), t1);
-  fp4_square(z2, z3, t0, t1);
-  fp4_square(z4, z5, t2, t3);
-  z4 = fp2_sub(t0, z4);
-  z4 = fp2_add(fp2_dbl(z4), t0);
-  z5 = fp2_add(t1, z5);
-  z5 = fp2_add(fp2_dbl(z5), t1);
-  t0 = fp2_mul_xi(t3);
-  z2 = fp2_add(t0, z2);
-  z2 = fp2_add(fp2_dbl(z2), t0);
-  z3 = fp2_sub(t2, z3);
-  z3 = fp2_add(fp2_dbl(z3), t2);
-  f = Fp12{Fp6{z0, z4, z3}, Fp6{z2, z1, z5}};
-}
-#endif
 SY_HD Fp12 cyclotomic_squared(const Fp12& f) {
   Fp12 r = f;
   cyclotomic_square_assign(r);

@@ -271,13 +271,10 @@ SY_HD_NOINLINE Fp12 fp12_inv(const Fp12& a) {
 
 // Multiplication by the sparse element l0 + l_vv v^2 + l_vw v w, i.e. slots z0, z2, z4 of
 // (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2).  Same 13-product schedule as fp12.rs:426-503.
-#ifndef SY_SPARSE_INPLACE
-#define SY_SPARSE_INPLACE 1
-#endif
-#if SY_SPARSE_INPLACE
 // In place (x0, x2, x4 must not alias f): the four products that need sums of z first, then every slot is overwritten as soon as its last reader is
 // done (z0 after z1 x2, z2 after z3 x4, z1 after z5 x4, z3 after z3 x0, z4 and z5 after z5 x2) - no result record and
-// no copy back (the one-record form stored the six outputs to the frame, re-loaded them and wrote f word by word).
+// no copy back (the one-record form stored the six outputs to the frame, re-loaded them and wrote f word by word:
+// k_miller 166.1 -> 162.7 ms per 2^20 without it, profiles/r02s_kbench_inplace.jsonl).
 SY_HD_NOINLINE void fp12_sparse_mul_assign(Fp12& f, const Fp2& x0, const Fp2& x4 /*ell_vw*/, const Fp2& x2 /*ell_vv*/) {
   Fp2 &z0 = f.c0.c0, &z1 = f.c0.c1, &z2 = f.c0.c2, &z3 = f.c1.c0, &z4 = f.c1.c1, &z5 = f.c1.c2;
   Fp2 x02 = fp2_add(x0, x2);
@@ -306,41 +303,6 @@ SY_HD_NOINLINE void fp12_sparse_mul_assign(Fp12& f, const Fp2& x0, const Fp2& x4
   z4 = fp2_mul_xi_add(t, fp2_sub(fp2_sub(p9, d0), d4));                        // r11
   z5 = fp2_sub(p10, s1);                                                       // r12
 }
-#else
-SY_HD_NOINLINE void fp12_sparse_mul_assign(Fp12& f, const Fp2& x0, const Fp2& x4 /*ell_vw*/, const Fp2& x2 /*ell_vv*/) {
-  const Fp2 &z0 = f.c0.c0, &z1 = f.c0.c1, &z2 = f.c0.c2, &z3 = f.c1.c0, &z4 = f.c1.c1, &z5 = f.c1.c2;
-  Fp12 r;  // every z is still read after the first outputs exist: collect them and store at the end
-  Fp2 d0 = fp2_mul(z0, x0);
-  Fp2 d2 = fp2_mul(z2, x2);
-  Fp2 d4 = fp2_mul(z4, x4);
-  Fp2 s1 = fp2_mul(z1, x2);
-  r.c0.c0 = fp2_mul_xi_add(fp2_add(s1, d4), d0);
-  Fp2 t3 = fp2_mul(z5, x4);
-  s1 = fp2_add(s1, t3);
-  Fp2 t4 = fp2_add(t3, d2);
-  t3 = fp2_mul(z1, x0);
-  s1 = fp2_add(s1, t3);
-  r.c0.c1 = fp2_mul_xi_add(t4, t3);
-  t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z2), fp2_add(x0, x2)), d0), d2);
-  t4 = fp2_mul(z3, x4);
-  s1 = fp2_add(s1, t4);
-  r.c0.c2 = fp2_add(t3, t4);
-  t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z2, z4), fp2_add(x2, x4)), d2), d4);
-  t4 = t3;
-  t3 = fp2_mul(z3, x0);
-  s1 = fp2_add(s1, t3);
-  r.c1.c0 = fp2_mul_xi_add(t4, t3);
-  t3 = fp2_mul(z5, x2);
-  s1 = fp2_add(s1, t3);
-  t4 = t3;
-  t3 = fp2_sub(fp2_sub(fp2_mul(fp2_add(z0, z4), fp2_add(x0, x4)), d0), d4);
-  r.c1.c1 = fp2_mul_xi_add(t4, t3);
-  Fp2 s0 = fp2_add(fp2_add(z1, z3), z5);
-  Fp2 t0 = fp2_add(fp2_add(x0, x2), x4);
-  r.c1.c2 = fp2_sub(fp2_mul(s0, t0), s1);
-  f = r;
-}
-#endif
 SY_HD Fp12 fp12_sparse_mul(const Fp12& f, const Fp2& x0, const Fp2& x4, const Fp2& x2) {
   Fp12 r = f;
   fp12_sparse_mul_assign(r, x0, x4, x2);
