@@ -271,8 +271,9 @@ SY_HD_NOINLINE Fp12 fp12_inv(const Fp12& a) {
 
 // Multiplication by the sparse element l0 + l_vv v^2 + l_vw v w, i.e. slots z0, z2, z4 of
 // (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2).  Same 13-product schedule as fp12.rs:426-503.
-// In place (x0, x2, x4 must not alias f): the four products that need sums of z first, then every slot is overwritten as soon as its last reader is
-// done (z0 after z1 x2, z2 after z3 x4, z1 after z5 x4, z3 after z3 x0, z4 and z5 after z5 x2) - no result record and
+// In place (x0, x2, x4 must not alias f): the four products that need sums of z first, then every slot is overwritten
+// as soon as its last reader is done (z0 after z1 x2, z2 after z3 x4, z1 after z5 x4, z3 after z3 x0, z4 and z5 after
+// z5 x2) - no result record and
 // no copy back (the one-record form stored the six outputs to the frame, re-loaded them and wrote f word by word:
 // k_miller 166.1 -> 162.7 ms per 2^20 without it, profiles/r02s_kbench_inplace.jsonl).
 SY_HD_NOINLINE void fp12_sparse_mul_assign(Fp12& f, const Fp2& x0, const Fp2& x4 /*ell_vw*/, const Fp2& x2 /*ell_vv*/) {
